@@ -1,0 +1,90 @@
+"""ctypes binding of ``include/owc_b200.h`` (the C-ABI shared library ``libowc_b200.so``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``nvcc -gencode
+arch=compute_100a,code=sm_100a``). There is no fallback: if the library is missing or a call fails
+the error propagates as :class:`OwcError`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+__all__ = ["lib", "OwcError", "OwcArch", "OwcStats", "OwcProfile", "KCATS", "check", "LIB_PATH", "PREC_BF16", "PREC_FP32",
+           "MEM_HOST", "MEM_DEVICE", "EXPORTS"]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libowc_b200.so")
+
+PREC_BF16, PREC_FP32 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class OwcError(RuntimeError):
+    """A C-ABI call returned non-zero; the message is ``owc_last_error()``."""
+
+
+class OwcArch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("layers", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32),
+                ("inter", C.c_int32), ("vocab", C.c_int32), ("max_pos", C.c_int32), ("type_vocab", C.c_int32),
+                ("pad_id", C.c_int32), ("ln_eps", C.c_float)]
+
+
+class OwcStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("tokens_encoded", C.c_int64), ("sequences_encoded", C.c_int64)]
+
+
+class OwcProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8)]
+
+
+KCATS = ("embed_ln", "gemm", "attn", "ln", "pool_l2", "sim_topk", "rescore", "misc")
+
+_P = C.c_void_p
+_I32, _I64 = C.c_int32, C.c_int64
+
+# name -> (restype, argtypes); every symbol include/owc_b200.h declares
+EXPORTS = {
+    "owc_abi_version": (_I32, []),
+    "owc_last_error": (C.c_char_p, []),
+    "owc_ctx_create": (_I32, [_I32, _P, _I32, C.POINTER(_P)]),
+    "owc_ctx_destroy": (_I32, [_P]),
+    "owc_ctx_sync": (_I32, [_P]),
+    "owc_ctx_stats": (_I32, [_P, C.POINTER(OwcStats)]),
+    "owc_ctx_profile_begin": (_I32, [_P]),
+    "owc_ctx_profile_end": (_I32, [_P, C.POINTER(OwcProfile)]),
+    "owc_encoder_load": (_I32, [_P, C.POINTER(OwcArch), _P, C.c_size_t, C.POINTER(_P)]),
+    "owc_encoder_destroy": (_I32, [_P]),
+    "owc_encode": (_I32, [_P, _P, _I32, _P, _I32, _I32, _P, _I32]),
+    "owc_pair_dot": (_I32, [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
+    "owc_sim_topk": (_I32, [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "owc_score": (_I32, [_P, _P, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32]),
+    "owc_debug_gemm": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "owc_bench_sim_kernel": (_I32, [_P, _I64, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library with typed signatures."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OwcError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(needs nvcc); there is no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.owc_abi_version() != 1:
+            raise OwcError("libowc_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise OwcError(lib().owc_last_error().decode("utf-8", "replace"))

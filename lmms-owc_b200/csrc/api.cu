@@ -1,0 +1,890 @@
+// api.cu - the C ABI declared in include/owc_b200.h: context, encoder, and the orchestration of
+// the kernels in kernels.cuh / gemm_tc.cuh on one CUDA stream. Host code only decides shapes,
+// chunking and launch order; all arithmetic happens in the kernels. No CPU fallback exists.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/owc_b200.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace owc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU_OK(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define OWC_TRY(expr)           \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct owc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int chunk_tokens = 0;
+  int sm_count = 0;
+  EncodeTiledFn encode_tiled = nullptr;
+  owc_stats stats{};
+  int* d_status = nullptr;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs: start, stop
+  std::vector<int> prof_cats;
+  size_t prof_used = 0;
+  // per-call scratch (grown on demand, reused across calls)
+  Buf ids, cu, targets, zp, zpb, zcb, zc32, cand_s, cand_i, out_s, out_i, out_p, tmp_a, tmp_b, tmp_c, tmp_d;
+};
+
+struct LayerW {
+  const float *bqkv, *bo, *ln1g, *ln1b, *b1, *b2, *ln2g, *ln2b;   // fp32 (device)
+  const float *wqkv32, *wo32, *w132, *w232;                        // fp32 masters (check mode)
+  const __nv_bfloat16 *wqkv, *wo, *w1, *w2;                        // bf16 operand copies
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+};
+
+struct owc_encoder {
+  owc_ctx* ctx = nullptr;
+  owc_arch arch{};
+  float* w32 = nullptr;            // the whole blob
+  __nv_bfloat16* w16 = nullptr;    // bf16 copies of the four GEMM weights of every layer
+  const float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr, *rel_lut = nullptr;
+  std::vector<LayerW> layers;
+  int cap = 0;                     // workspace rows (tokens per chunk)
+  float *x = nullptr, *y = nullptr;
+  __nv_bfloat16 *xb = nullptr, *qkv = nullptr, *ao = nullptr, *f = nullptr;
+  float *qkv32 = nullptr, *ao32 = nullptr, *f32 = nullptr;   // check mode, allocated on first use
+  CUtensorMap tm_xb, tm_ao, tm_f;
+};
+
+constexpr int kEncBN = 192;   // divides 3H, H and I of both architectures (1152/384/1536, 2304/768/3072)
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+static int ensure(owc_ctx* c, Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  CU_OK(cudaStreamSynchronize(c->stream));  // earlier launches may still read the old buffer
+  if (b.p) CU_OK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  CU_OK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+static int to_device(owc_ctx* c, Buf& b, const void* src, size_t bytes, int space, const void** dptr) {
+  if (space == OWC_MEM_DEVICE) { *dptr = src; return 0; }
+  OWC_TRY(ensure(c, b, bytes));
+  CU_OK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += static_cast<int64_t>(bytes);
+  *dptr = b.p;
+  return 0;
+}
+
+static int from_device(owc_ctx* c, void* dst, const void* src, size_t bytes, int space) {
+  if (space == OWC_MEM_DEVICE) {
+    if (dst != src) CU_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
+  CU_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += static_cast<int64_t>(bytes);
+  return 0;
+}
+
+// Brackets one kernel launch with CUDA events while profiling is on (owc_ctx_profile_begin/end).
+struct ProfScope {
+  owc_ctx* c;
+  cudaEvent_t stop = nullptr;
+  ProfScope(owc_ctx* ctx, int cat) : c(ctx) {
+    if (!c->profiling) return;
+    if (c->prof_used + 2 > c->prof_events.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->prof_events.push_back(a);
+      c->prof_events.push_back(b);
+    }
+    cudaEventRecord(c->prof_events[c->prof_used], c->stream);
+    stop = c->prof_events[c->prof_used + 1];
+    c->prof_used += 2;
+    c->prof_cats.push_back(cat);
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
+
+static int check_launch(owc_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+  c->stats.kernel_launches += 1;
+  return 0;
+}
+
+// K-major bf16 matrix [rows, cols] -> 2-D tiled tensor map, box = 64 cols x box_rows, SWIZZLE_128B.
+static int make_tmap(owc_ctx* c, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("tensor map base not 16-byte aligned");
+  if (cols % 64 != 0) return fail("tensor map inner dimension %llu is not a multiple of 64", (unsigned long long)cols);
+  if (rows == 0) rows = 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+template <int BN, int EPI, int KC>
+static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs g, int splits) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_OK(cudaFuncSetAttribute(k_gemm_tc<BN, EPI, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  if (g.K % 64 != 0 || g.K <= 0) return fail("tcgen05 GEMM needs K %% 64 == 0 (K=%d)", g.K);
+  if (EPI != EPI_TOPK && g.N % 32 != 0) return fail("tcgen05 GEMM needs N %% 32 == 0 (N=%d)", g.N);
+  const int tiles = (g.N + BN - 1) / BN;
+  splits = std::max(1, std::min(splits, tiles));
+  g.tiles_per_cta = (tiles + splits - 1) / splits;
+  const int gy = (tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  dim3 grid((g.M + 127) / 128, gy);
+  ProfScope prof(c, EPI == EPI_TOPK ? OWC_KCAT_SIM : OWC_KCAT_GEMM);
+  k_gemm_tc<BN, EPI, KC><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, g);
+  return check_launch(c, "k_gemm_tc");
+}
+
+// column splits so that (row blocks x splits) covers the SMs when there are few row blocks
+static int pick_splits(const owc_ctx* c, int m, int n, int bn) {
+  const int mb = (m + 127) / 128, tiles = (n + bn - 1) / bn;
+  if (mb >= c->sm_count) return 1;
+  return std::max(1, std::min(tiles, (c->sm_count + mb - 1) / mb));
+}
+
+template <int EPF>
+static int launch_gemm_f32(owc_ctx* c, const float* A, const float* W, const float* bias, const float* res, float* out,
+                           int M, int N, int K, int ldo) {
+  if (K % 16 != 0) return fail("fp32 GEMM needs K %% 16 == 0 (K=%d)", K);
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  ProfScope prof(c, OWC_KCAT_GEMM);
+  k_gemm_f32<EPF><<<grid, 256, 0, c->stream>>>(A, W, bias, res, out, M, N, K, ldo);
+  return check_launch(c, "k_gemm_f32");
+}
+
+static int launch_convert(owc_ctx* c, const float* in, __nv_bfloat16* out, long long n) {
+  if (n <= 0) return 0;
+  const long long threads = (n + 3) / 4;
+  ProfScope prof(c, OWC_KCAT_MISC);
+  k_f32_to_bf16<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(in, out, n);
+  return check_launch(c, "k_f32_to_bf16");
+}
+
+#define DISPATCH_NV(H, ...)                                           \
+  switch ((H) / 128) {                                                \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break;             \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break;             \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break;             \
+    case 6: { constexpr int NV = 6; __VA_ARGS__; } break;             \
+    case 8: { constexpr int NV = 8; __VA_ARGS__; } break;             \
+    default: return fail("hidden size %d unsupported (need 256/384/512/768/1024)", (H)); \
+  }
+
+// ------------------------------------------------------------------------------------------------
+// ABI: misc
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t owc_abi_version(void) { return OWC_ABI_VERSION; }
+extern "C" const char* owc_last_error(void) { return g_err; }
+
+extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_tokens, owc_ctx** out) {
+  if (!out) return fail("owc_ctx_create: out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail("device %d out of range (have %d)", device, n_dev);
+  CU_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  owc_ctx* c = new (std::nothrow) owc_ctx();
+  if (!c) return fail("out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
+  if (stream) {
+    c->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
+    c->own_stream = true;
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    delete c;
+    return fail("cuTensorMapEncodeTiled not available from the driver");
+  }
+  c->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaMalloc(&c->d_status, sizeof(int)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
+  cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
+  *out = c;
+  return 0;
+}
+
+extern "C" int32_t owc_ctx_destroy(owc_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  Buf* bufs[] = {&c->ids, &c->cu, &c->targets, &c->zp, &c->zpb, &c->zcb, &c->zc32, &c->cand_s, &c->cand_i,
+                 &c->out_s, &c->out_i, &c->out_p, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->d_status) cudaFree(c->d_status);
+  for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+static int sync_and_check(owc_ctx* c) {
+  int status = 0;
+  CU_OK(cudaMemcpyAsync(&status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  if (status != 0) {
+    cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
+    return fail("token id out of range for the embedding table (status %d)", status);
+  }
+  return 0;
+}
+
+extern "C" int32_t owc_ctx_sync(owc_ctx* c) {
+  if (!c) return fail("ctx is NULL");
+  CU_OK(cudaSetDevice(c->device));
+  return sync_and_check(c);
+}
+
+extern "C" int32_t owc_ctx_stats(owc_ctx* c, owc_stats* out) {
+  if (!c || !out) return fail("NULL argument");
+  *out = c->stats;
+  return 0;
+}
+
+extern "C" int32_t owc_ctx_profile_begin(owc_ctx* c) {
+  if (!c) return fail("ctx is NULL");
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  c->prof_used = 0;
+  c->prof_cats.clear();
+  c->profiling = true;
+  return 0;
+}
+
+extern "C" int32_t owc_ctx_profile_end(owc_ctx* c, owc_profile* out) {
+  if (!c || !out) return fail("NULL argument");
+  CU_OK(cudaSetDevice(c->device));
+  c->profiling = false;
+  CU_OK(cudaStreamSynchronize(c->stream));
+  memset(out, 0, sizeof(*out));
+  for (size_t i = 0; i < c->prof_cats.size(); ++i) {
+    float ms = 0.f;
+    CU_OK(cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]));
+    out->ms[c->prof_cats[i]] += ms;
+    out->launches[c->prof_cats[i]] += 1;
+  }
+  c->prof_used = 0;
+  c->prof_cats.clear();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: encoder load / destroy
+// ------------------------------------------------------------------------------------------------
+static size_t blob_floats(const owc_arch& a) {
+  const size_t h = a.hidden, i = a.inter;
+  size_t n = (size_t)a.vocab * h + (size_t)a.max_pos * h + (size_t)a.type_vocab * h + 2 * h;
+  if (a.kind == OWC_ARCH_MPNET) n += (size_t)a.heads * (2 * (size_t)a.max_pos - 1);
+  const size_t per_layer = 3 * h * h + 3 * h + h * h + h + 2 * h + i * h + i + h * i + h + 2 * h;
+  return n + (size_t)a.layers * per_layer;
+}
+
+extern "C" int32_t owc_encoder_destroy(owc_encoder* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete e;
+  return 0;
+}
+
+extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const float* weights, size_t n_floats,
+                                    owc_encoder** out) {
+  if (!c || !arch || !weights || !out) return fail("owc_encoder_load: NULL argument");
+  *out = nullptr;
+  const owc_arch& a = *arch;
+  if (a.kind != OWC_ARCH_BERT && a.kind != OWC_ARCH_MPNET) return fail("unknown arch kind %d", a.kind);
+  if (a.hidden % 128 != 0 || a.hidden < 256 || a.hidden > 1024) return fail("hidden %d unsupported", a.hidden);
+  if (a.heads <= 0 || a.hidden % a.heads != 0) return fail("heads %d does not divide hidden %d", a.heads, a.hidden);
+  const int hd = a.hidden / a.heads;
+  if (hd != 32 && hd != 64) return fail("head_dim %d unsupported (need 32 or 64)", hd);
+  if (a.inter % 64 != 0 || a.layers <= 0 || a.vocab <= 0 || a.max_pos <= 0) return fail("bad architecture constants");
+  if (a.kind == OWC_ARCH_BERT && a.type_vocab < 1) return fail("BERT needs a token-type table");
+  if (a.kind == OWC_ARCH_MPNET && (a.type_vocab != 0 || a.heads % 4 != 0)) return fail("bad MPNet constants");
+  if (n_floats != blob_floats(a)) return fail("weight blob has %zu floats, architecture needs %zu", n_floats, blob_floats(a));
+  CU_OK(cudaSetDevice(c->device));
+
+  owc_encoder* e = new (std::nothrow) owc_encoder();
+  if (!e) return fail("out of host memory");
+  e->ctx = c;
+  e->arch = a;
+  e->cap = c->chunk_tokens;
+  const size_t h = a.hidden, I = a.inter;
+#define LOAD_FAIL(...) do { int _r = fail(__VA_ARGS__); owc_encoder_destroy(e); return _r; } while (0)
+#define LOAD_CU(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) LOAD_FAIL("%s failed: %s", #expr, cudaGetErrorString(_e)); } while (0)
+  LOAD_CU(cudaMalloc(&e->w32, n_floats * sizeof(float)));
+  LOAD_CU(cudaMemcpyAsync(e->w32, weights, n_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += static_cast<int64_t>(n_floats * sizeof(float));
+  const size_t per_layer16 = 3 * h * h + h * h + I * h + h * I;
+  LOAD_CU(cudaMalloc(&e->w16, a.layers * per_layer16 * sizeof(__nv_bfloat16)));
+
+  const float* p = e->w32;
+  e->word = p; p += (size_t)a.vocab * h;
+  e->pos = p; p += (size_t)a.max_pos * h;
+  if (a.kind == OWC_ARCH_BERT) { e->type0 = p; p += (size_t)a.type_vocab * h; }
+  e->emb_g = p; p += h;
+  e->emb_b = p; p += h;
+  if (a.kind == OWC_ARCH_MPNET) { e->rel_lut = p; p += (size_t)a.heads * (2 * (size_t)a.max_pos - 1); }
+  e->layers.resize(a.layers);
+  __nv_bfloat16* q = e->w16;
+  for (int l = 0; l < a.layers; ++l) {
+    LayerW& L = e->layers[l];
+    L.wqkv32 = p; p += 3 * h * h;
+    L.bqkv = p; p += 3 * h;
+    L.wo32 = p; p += h * h;
+    L.bo = p; p += h;
+    L.ln1g = p; p += h;
+    L.ln1b = p; p += h;
+    L.w132 = p; p += I * h;
+    L.b1 = p; p += I;
+    L.w232 = p; p += h * I;
+    L.b2 = p; p += h;
+    L.ln2g = p; p += h;
+    L.ln2b = p; p += h;
+    L.wqkv = q; q += 3 * h * h;
+    L.wo = q; q += h * h;
+    L.w1 = q; q += I * h;
+    L.w2 = q; q += h * I;
+    if (launch_convert(c, L.wqkv32, const_cast<__nv_bfloat16*>(L.wqkv), 3 * h * h) ||
+        launch_convert(c, L.wo32, const_cast<__nv_bfloat16*>(L.wo), h * h) ||
+        launch_convert(c, L.w132, const_cast<__nv_bfloat16*>(L.w1), I * h) ||
+        launch_convert(c, L.w232, const_cast<__nv_bfloat16*>(L.w2), h * I)) { owc_encoder_destroy(e); return 1; }
+    if (make_tmap(c, &L.tm_wqkv, L.wqkv, 3 * h, h, kEncBN) || make_tmap(c, &L.tm_wo, L.wo, h, h, kEncBN) ||
+        make_tmap(c, &L.tm_w1, L.w1, I, h, kEncBN) || make_tmap(c, &L.tm_w2, L.w2, h, I, kEncBN)) { owc_encoder_destroy(e); return 1; }
+  }
+  if (static_cast<size_t>(p - e->w32) != n_floats) LOAD_FAIL("internal: blob walk mismatch");
+
+  const size_t cap = e->cap;
+  LOAD_CU(cudaMalloc(&e->x, cap * h * sizeof(float)));
+  LOAD_CU(cudaMalloc(&e->y, cap * h * sizeof(float)));
+  LOAD_CU(cudaMalloc(&e->xb, cap * h * sizeof(__nv_bfloat16)));
+  LOAD_CU(cudaMalloc(&e->qkv, cap * 3 * h * sizeof(__nv_bfloat16)));
+  LOAD_CU(cudaMalloc(&e->ao, cap * h * sizeof(__nv_bfloat16)));
+  LOAD_CU(cudaMalloc(&e->f, cap * I * sizeof(__nv_bfloat16)));
+  // Rows past a chunk's token count are read by TMA (never stored): keep them finite.
+  LOAD_CU(cudaMemsetAsync(e->xb, 0, cap * h * sizeof(__nv_bfloat16), c->stream));
+  LOAD_CU(cudaMemsetAsync(e->ao, 0, cap * h * sizeof(__nv_bfloat16), c->stream));
+  LOAD_CU(cudaMemsetAsync(e->f, 0, cap * I * sizeof(__nv_bfloat16), c->stream));
+  if (make_tmap(c, &e->tm_xb, e->xb, cap, h, 128) || make_tmap(c, &e->tm_ao, e->ao, cap, h, 128) ||
+      make_tmap(c, &e->tm_f, e->f, cap, I, 128)) { owc_encoder_destroy(e); return 1; }
+  LOAD_CU(cudaStreamSynchronize(c->stream));  // `weights` may be freed by the caller after return
+#undef LOAD_CU
+#undef LOAD_FAIL
+  *out = e;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder forward over one chunk of whole sequences
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_attn(owc_encoder* e, const AttnArgs& aa) {
+  owc_ctx* c = e->ctx;
+  const int D = e->arch.hidden / e->arch.heads;
+  const long long pairs = static_cast<long long>(aa.n_seq) * aa.heads;
+  const bool is_short = aa.max_t <= 64;
+  const int groups = is_short ? 4 : 1;
+  const size_t smem = (static_cast<size_t>(groups) * aa.max_t * (D + 1) + 4 * D + 4 * static_cast<size_t>(aa.max_t)) * sizeof(float);
+  const unsigned grid = static_cast<unsigned>((pairs + groups - 1) / groups);
+  ProfScope prof(c, OWC_KCAT_ATTN);
+#define ATTN_LAUNCH(DD, WPP, KPL)                                                                         \
+  do {                                                                                                    \
+    static size_t smem_set = 0;                                                                           \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                            \
+      CU_OK(cudaFuncSetAttribute(k_attn<T, DD, WPP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                    \
+    }                                                                                                     \
+    k_attn<T, DD, WPP, KPL><<<grid, 128, smem, c->stream>>>(aa);                                          \
+  } while (0)
+  if (D == 32) {
+    if (aa.max_t <= 32) ATTN_LAUNCH(32, 1, 1);
+    else if (is_short) ATTN_LAUNCH(32, 1, 2);
+    else ATTN_LAUNCH(32, 4, 16);
+  } else {
+    if (aa.max_t <= 32) ATTN_LAUNCH(64, 1, 1);
+    else if (is_short) ATTN_LAUNCH(64, 1, 2);
+    else ATTN_LAUNCH(64, 4, 16);
+  }
+#undef ATTN_LAUNCH
+  return check_launch(c, "k_attn");
+}
+
+static int ensure_f32_workspace(owc_encoder* e) {
+  if (e->qkv32) return 0;
+  const size_t cap = e->cap, h = e->arch.hidden, I = e->arch.inter;
+  CU_OK(cudaMalloc(&e->qkv32, cap * 3 * h * sizeof(float)));
+  CU_OK(cudaMalloc(&e->ao32, cap * h * sizeof(float)));
+  CU_OK(cudaMalloc(&e->f32, cap * I * sizeof(float)));
+  return 0;
+}
+
+// ids/cu: device copies for the whole call. Sequences [seq0, seq0+n_seq), tokens [tok0, tok0+M).
+static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, int seq0, int n_seq, int tok0, int M,
+                        int max_t, int precision, float* z, __nv_bfloat16* zb) {
+  owc_ctx* c = e->ctx;
+  const owc_arch& a = e->arch;
+  const int H = a.hidden, I = a.inter;
+  const bool bf = precision == OWC_PREC_BF16;
+  if (!bf) OWC_TRY(ensure_f32_workspace(e));
+
+  EmbedArgs ea{};
+  ea.ids = d_ids; ea.cu = d_cu; ea.seq0 = seq0; ea.n_seq = n_seq; ea.tok0 = tok0;
+  ea.word = e->word; ea.pos = e->pos; ea.type0 = e->type0; ea.gamma = e->emb_g; ea.beta = e->emb_b;
+  ea.eps = a.ln_eps; ea.H = H; ea.vocab = a.vocab; ea.max_pos = a.max_pos;
+  ea.mpnet = a.kind == OWC_ARCH_MPNET; ea.pad_id = a.pad_id;
+  ea.x = e->x; ea.xb = bf ? e->xb : nullptr; ea.status = c->d_status;
+  {
+    ProfScope prof(c, OWC_KCAT_EMBED);
+    DISPATCH_NV(H, k_embed_ln<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(ea));
+  }
+  OWC_TRY(check_launch(c, "k_embed_ln"));
+
+  AttnArgs aa{};
+  aa.cu = d_cu; aa.seq0 = seq0; aa.n_seq = n_seq; aa.tok0 = tok0; aa.H = H; aa.heads = a.heads; aa.max_t = max_t;
+  aa.scale = 1.0f / sqrtf(static_cast<float>(H / a.heads));
+  aa.rel_lut = e->rel_lut; aa.max_pos = a.max_pos;
+
+  const int ln_grid = (M + 7) / 8;
+  for (int l = 0; l < a.layers; ++l) {
+    const LayerW& L = e->layers[l];
+    if (bf) {
+      GemmArgs g{};
+      g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = e->qkv; g.ldo = 3 * H;
+      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, e->tm_xb, L.tm_wqkv, g, pick_splits(c, M, g.N, kEncBN))));
+      aa.qkv = e->qkv; aa.out = e->ao;
+      OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
+      g = GemmArgs{};
+      g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = e->x; g.out = e->y; g.ldo = H;
+      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, g, pick_splits(c, M, g.N, kEncBN))));
+    } else {
+      OWC_TRY(launch_gemm_f32<EPF_BIAS>(c, e->x, L.wqkv32, L.bqkv, nullptr, e->qkv32, M, 3 * H, H, 3 * H));
+      aa.qkv = e->qkv32; aa.out = e->ao32;
+      OWC_TRY(launch_attn<float>(e, aa));
+      OWC_TRY(launch_gemm_f32<EPF_BIAS_RES>(c, e->ao32, L.wo32, L.bo, e->x, e->y, M, H, H, H));
+    }
+    {
+      ProfScope prof(c, OWC_KCAT_LN);
+      DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln1g, L.ln1b, a.ln_eps, e->x, bf ? e->xb : nullptr));
+    }
+    OWC_TRY(check_launch(c, "k_ln"));
+    if (bf) {
+      GemmArgs g{};
+      g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = e->f; g.ldo = I;
+      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, e->tm_xb, L.tm_w1, g, pick_splits(c, M, g.N, kEncBN))));
+      g = GemmArgs{};
+      g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = e->x; g.out = e->y; g.ldo = H;
+      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, g, pick_splits(c, M, g.N, kEncBN))));
+    } else {
+      OWC_TRY(launch_gemm_f32<EPF_BIAS_GELU>(c, e->x, L.w132, L.b1, nullptr, e->f32, M, I, H, I));
+      OWC_TRY(launch_gemm_f32<EPF_BIAS_RES>(c, e->f32, L.w232, L.b2, e->x, e->y, M, H, I, H));
+    }
+    const bool last = l + 1 == a.layers;
+    {
+      ProfScope prof(c, OWC_KCAT_LN);
+      DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln2g, L.ln2b, a.ln_eps, e->x, (bf && !last) ? e->xb : nullptr));
+    }
+    OWC_TRY(check_launch(c, "k_ln"));
+  }
+  {
+    ProfScope prof(c, OWC_KCAT_POOL);
+    DISPATCH_NV(H, k_pool_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->x, d_cu, seq0, n_seq, tok0, H, z, zb));
+  }
+  OWC_TRY(check_launch(c, "k_pool_l2"));
+  c->stats.tokens_encoded += M;
+  c->stats.sequences_encoded += n_seq;
+  return 0;
+}
+
+// Validates cu_seqlens, stages ids/cu on the device and runs every chunk. z: device fp32 [n_seq,H];
+// zb: device bf16 [n_seq,H] or nullptr.
+static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const int32_t* cu, int n_seq, int precision,
+                      float* z, __nv_bfloat16* zb) {
+  owc_ctx* c = e->ctx;
+  if (precision != OWC_PREC_BF16 && precision != OWC_PREC_FP32) return fail("unknown precision %d", precision);
+  if (n_seq < 0 || !cu) return fail("bad cu_seqlens");
+  if (n_seq == 0) return 0;
+  if (cu[0] != 0) return fail("cu_seqlens[0] must be 0");
+  const int max_len = e->arch.kind == OWC_ARCH_MPNET ? e->arch.max_pos - 2 : e->arch.max_pos;
+  for (int s = 0; s < n_seq; ++s) {
+    const int len = cu[s + 1] - cu[s];
+    if (len < 0) return fail("cu_seqlens decreases at %d", s);
+    if (len > max_len) return fail("sequence %d has %d tokens; the position table allows %d (truncate on the host)", s, len, max_len);
+  }
+  const long long total = cu[n_seq];
+  if (total > 0 && !ids) return fail("ids is NULL");
+  const void* d_ids = nullptr;
+  const void* d_cu = nullptr;
+  OWC_TRY(to_device(c, c->ids, ids, static_cast<size_t>(std::max<long long>(total, 1)) * sizeof(int32_t), ids_space, &d_ids));
+  OWC_TRY(to_device(c, c->cu, cu, (static_cast<size_t>(n_seq) + 1) * sizeof(int32_t), OWC_MEM_HOST, &d_cu));
+  int s0 = 0;
+  while (s0 < n_seq) {
+    int s1 = s0, max_t = 1;
+    while (s1 < n_seq && cu[s1 + 1] - cu[s0] <= e->cap) {
+      max_t = std::max(max_t, cu[s1 + 1] - cu[s1]);
+      ++s1;
+    }
+    if (s1 == s0) return fail("internal: chunk capacity %d below one sequence", e->cap);
+    OWC_TRY(encode_chunk(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), s0, s1 - s0, cu[s0],
+                         cu[s1] - cu[s0], max_t, precision, z, zb));
+    s0 = s1;
+  }
+  return 0;
+}
+
+extern "C" int32_t owc_encode(owc_encoder* e, const int32_t* ids, int32_t ids_space, const int32_t* cu, int32_t n_seq,
+                              int32_t precision, float* out, int32_t out_space) {
+  if (!e || !out) return fail("owc_encode: NULL argument");
+  owc_ctx* c = e->ctx;
+  CU_OK(cudaSetDevice(c->device));
+  if (n_seq == 0) return 0;
+  const size_t bytes = static_cast<size_t>(n_seq) * e->arch.hidden * sizeof(float);
+  float* z = out;
+  if (out_space == OWC_MEM_HOST) {
+    OWC_TRY(ensure(c, c->zp, bytes));
+    z = static_cast<float*>(c->zp.p);
+  }
+  OWC_TRY(encode_all(e, ids, ids_space, cu, n_seq, precision, z, nullptr));
+  if (out_space == OWC_MEM_HOST) {
+    OWC_TRY(from_device(c, out, z, bytes, OWC_MEM_HOST));
+    return sync_and_check(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: paired dot
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t owc_pair_dot(owc_ctx* c, const float* a, int64_t na, const int32_t* a_index, const float* b, int64_t nb,
+                                const int32_t* b_index, int64_t n, int32_t dim, int32_t space, float* out) {
+  if (!c || !a || !b || !out) return fail("owc_pair_dot: NULL argument");
+  if (n < 0 || na < 0 || nb < 0 || dim <= 0 || dim % 4 != 0) return fail("owc_pair_dot: bad n/dim");
+  if ((!a_index && na != n) || (!b_index && nb != n)) return fail("owc_pair_dot: without an index the table must have n rows");
+  if (n == 0) return 0;
+  CU_OK(cudaSetDevice(c->device));
+  const void *da, *db, *dai = nullptr, *dbi = nullptr;
+  OWC_TRY(to_device(c, c->tmp_a, a, static_cast<size_t>(na) * dim * sizeof(float), space, &da));
+  OWC_TRY(to_device(c, c->tmp_b, b, static_cast<size_t>(nb) * dim * sizeof(float), space, &db));
+  if (a_index) OWC_TRY(to_device(c, c->tmp_c, a_index, static_cast<size_t>(n) * sizeof(int32_t), space, &dai));
+  if (b_index) OWC_TRY(to_device(c, c->tmp_d, b_index, static_cast<size_t>(n) * sizeof(int32_t), space, &dbi));
+  float* dout = out;
+  if (space == OWC_MEM_HOST) {
+    OWC_TRY(ensure(c, c->out_p, static_cast<size_t>(n) * sizeof(float)));
+    dout = static_cast<float*>(c->out_p.p);
+  }
+  ProfScope prof(c, OWC_KCAT_RESCORE);
+  k_pair_dot<<<static_cast<unsigned>((n + 7) / 8), 256, 0, c->stream>>>(
+      static_cast<const float*>(da), static_cast<const int32_t*>(dai), static_cast<const float*>(db),
+      static_cast<const int32_t*>(dbi), n, dim, dout);
+  OWC_TRY(check_launch(c, "k_pair_dot"));
+  if (space == OWC_MEM_HOST) {
+    OWC_TRY(from_device(c, out, dout, static_cast<size_t>(n) * sizeof(float), OWC_MEM_HOST));
+    return sync_and_check(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// similarity + top-k on device-resident embeddings
+// ------------------------------------------------------------------------------------------------
+template <int BN, int KC>
+static int sim_candidates(owc_ctx* c, const __nv_bfloat16* zpb, long long n, const __nv_bfloat16* zcb, int C, int dim,
+                          int* splits_out) {
+  CUtensorMap ta, tb;
+  OWC_TRY(make_tmap(c, &ta, zpb, static_cast<uint64_t>(n), dim, 128));
+  OWC_TRY(make_tmap(c, &tb, zcb, static_cast<uint64_t>(C), dim, BN));
+  int splits = pick_splits(c, static_cast<int>(n), C, BN);
+  splits = std::min(splits, 128 / KC);
+  const int tiles = (C + BN - 1) / BN;
+  splits = std::max(1, std::min(splits, tiles));
+  const int tpc = (tiles + splits - 1) / splits;
+  splits = (tiles + tpc - 1) / tpc;
+  OWC_TRY(ensure(c, c->cand_s, static_cast<size_t>(splits) * n * KC * sizeof(float)));
+  OWC_TRY(ensure(c, c->cand_i, static_cast<size_t>(splits) * n * KC * sizeof(int)));
+  GemmArgs g{};
+  g.M = static_cast<int>(n); g.N = C; g.K = dim;
+  g.cand_score = static_cast<float*>(c->cand_s.p);
+  g.cand_idx = static_cast<int*>(c->cand_i.p);
+  OWC_TRY((launch_gemm_tc<BN, EPI_TOPK, KC>(c, ta, tb, g, splits)));
+  *splits_out = splits;
+  return 0;
+}
+
+// zp/zc fp32 device; zpb/zcb bf16 device copies (bf16 mode). Outputs device.
+static int sim_topk_device(owc_ctx* c, const float* zp, const __nv_bfloat16* zpb, long long n, const float* zc,
+                           const __nv_bfloat16* zcb, int C, int dim, int k, int precision, const int32_t* targets,
+                           float* d_scores, int32_t* d_idx, float* d_paired) {
+  if (k < 1 || k > 16 || k > C) return fail("top-k needs 1 <= k <= min(16, c) (k=%d, c=%d)", k, C);
+  if (n >= (1LL << 31)) return fail("too many rows (%lld)", n);
+  if (n == 0) return 0;
+  if (precision == OWC_PREC_BF16) {
+    if (dim % 64 != 0) return fail("bf16 similarity needs dim %% 64 == 0 (dim=%d)", dim);
+    const int KC = (k <= 5) ? 8 : 16;   // candidates kept per row before the exact fp32 re-score
+    int splits = 1;
+    if (C <= 128) {
+      if (KC == 8) OWC_TRY((sim_candidates<128, 8>(c, zpb, n, zcb, C, dim, &splits)));
+      else OWC_TRY((sim_candidates<128, 16>(c, zpb, n, zcb, C, dim, &splits)));
+    } else {
+      if (KC == 8) OWC_TRY((sim_candidates<256, 8>(c, zpb, n, zcb, C, dim, &splits)));
+      else OWC_TRY((sim_candidates<256, 16>(c, zpb, n, zcb, C, dim, &splits)));
+    }
+    const size_t smem = 4 * 2 * static_cast<size_t>(splits) * KC * sizeof(float);
+    ProfScope prof(c, OWC_KCAT_RESCORE);
+    k_rescore<<<static_cast<unsigned>((n + 3) / 4), 128, smem, c->stream>>>(zp, zc, n, dim, static_cast<const int*>(c->cand_i.p),
+                                                                            splits, KC, k, targets, d_scores, d_idx, d_paired);
+    return check_launch(c, "k_rescore");
+  }
+  // check mode: materialise fp32 score rows in slabs, then top-k per row
+  const long long slab_rows = std::max<long long>(64, std::min<long long>(n, (256LL << 20) / (static_cast<long long>(C) * 4)));
+  OWC_TRY(ensure(c, c->tmp_c, static_cast<size_t>(slab_rows) * C * sizeof(float)));
+  float* S = static_cast<float*>(c->tmp_c.p);
+  for (long long r0 = 0; r0 < n; r0 += slab_rows) {
+    const int rows = static_cast<int>(std::min(slab_rows, n - r0));
+    OWC_TRY(launch_gemm_f32<EPF_BIAS>(c, zp + r0 * dim, zc, nullptr, nullptr, S, rows, C, dim, C));
+    const size_t smem = 4 * 2 * 32 * 16 * sizeof(float);
+    ProfScope prof(c, OWC_KCAT_RESCORE);
+    k_topk_rows<16><<<(rows + 3) / 4, 128, smem, c->stream>>>(S, rows, C, k, d_scores + r0 * k, d_idx + r0 * k);
+    OWC_TRY(check_launch(c, "k_topk_rows"));
+  }
+  if (targets && d_paired) {
+    ProfScope prof(c, OWC_KCAT_RESCORE);
+    k_pair_dot<<<static_cast<unsigned>((n + 7) / 8), 256, 0, c->stream>>>(zc, targets, zp, nullptr, n, dim, d_paired);
+    OWC_TRY(check_launch(c, "k_pair_dot"));
+  }
+  return 0;
+}
+
+extern "C" int32_t owc_sim_topk(owc_ctx* c, const float* zp, int64_t n, const float* zc, int32_t C, int32_t dim, int32_t k,
+                                int32_t precision, int32_t space, float* scores, int32_t* idx) {
+  if (!c || !zp || !zc || !scores || !idx) return fail("owc_sim_topk: NULL argument");
+  if (n < 0 || C <= 0 || dim <= 0 || dim % 4 != 0) return fail("owc_sim_topk: bad shape");
+  if (n == 0) return 0;
+  CU_OK(cudaSetDevice(c->device));
+  const void *dzp, *dzc;
+  OWC_TRY(to_device(c, c->tmp_a, zp, static_cast<size_t>(n) * dim * sizeof(float), space, &dzp));
+  OWC_TRY(to_device(c, c->zc32, zc, static_cast<size_t>(C) * dim * sizeof(float), space, &dzc));
+  const __nv_bfloat16 *zpb = nullptr, *zcb = nullptr;
+  if (precision == OWC_PREC_BF16) {
+    OWC_TRY(ensure(c, c->zpb, static_cast<size_t>(n) * dim * 2));
+    OWC_TRY(ensure(c, c->zcb, static_cast<size_t>(C) * dim * 2));
+    OWC_TRY(launch_convert(c, static_cast<const float*>(dzp), static_cast<__nv_bfloat16*>(c->zpb.p), n * dim));
+    OWC_TRY(launch_convert(c, static_cast<const float*>(dzc), static_cast<__nv_bfloat16*>(c->zcb.p), static_cast<long long>(C) * dim));
+    zpb = static_cast<const __nv_bfloat16*>(c->zpb.p);
+    zcb = static_cast<const __nv_bfloat16*>(c->zcb.p);
+  }
+  float* ds = scores;
+  int32_t* di = idx;
+  if (space == OWC_MEM_HOST) {
+    OWC_TRY(ensure(c, c->out_s, static_cast<size_t>(n) * k * sizeof(float)));
+    OWC_TRY(ensure(c, c->out_i, static_cast<size_t>(n) * k * sizeof(int32_t)));
+    ds = static_cast<float*>(c->out_s.p);
+    di = static_cast<int32_t*>(c->out_i.p);
+  }
+  OWC_TRY(sim_topk_device(c, static_cast<const float*>(dzp), zpb, n, static_cast<const float*>(dzc), zcb, C, dim, k,
+                          precision, nullptr, ds, di, nullptr));
+  if (space == OWC_MEM_HOST) {
+    OWC_TRY(from_device(c, scores, ds, static_cast<size_t>(n) * k * sizeof(float), OWC_MEM_HOST));
+    OWC_TRY(from_device(c, idx, di, static_cast<size_t>(n) * k * sizeof(int32_t), OWC_MEM_HOST));
+    return sync_and_check(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: the whole path for one shard
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t owc_score(owc_encoder* e, const int32_t* ids, int32_t ids_space, const int32_t* cu, int32_t n_seq,
+                             const float* zc, int32_t C, const int32_t* targets, int32_t k, int32_t precision,
+                             float* out_scores, int32_t* out_idx, float* out_paired, float* out_embeds, int32_t out_space) {
+  if (!e || !zc || !out_scores || !out_idx) return fail("owc_score: NULL argument");
+  owc_ctx* c = e->ctx;
+  CU_OK(cudaSetDevice(c->device));
+  if (n_seq == 0) return 0;
+  if (C <= 0) return fail("owc_score: no classes");
+  const int H = e->arch.hidden;
+  const size_t n = static_cast<size_t>(n_seq);
+  const bool host_out = out_space == OWC_MEM_HOST;
+  const bool bf = precision == OWC_PREC_BF16;
+
+  float* z = (out_embeds && !host_out) ? out_embeds : nullptr;
+  if (!z) {
+    OWC_TRY(ensure(c, c->zp, n * H * sizeof(float)));
+    z = static_cast<float*>(c->zp.p);
+  }
+  __nv_bfloat16* zb = nullptr;
+  if (bf) {
+    OWC_TRY(ensure(c, c->zpb, n * H * 2));
+    OWC_TRY(ensure(c, c->zcb, static_cast<size_t>(C) * H * 2));
+    zb = static_cast<__nv_bfloat16*>(c->zpb.p);
+  }
+  const void* d_targets = nullptr;
+  if (targets) OWC_TRY(to_device(c, c->targets, targets, n * sizeof(int32_t), ids_space, &d_targets));
+  float *ds = out_scores, *dp = out_paired;
+  int32_t* di = out_idx;
+  if (host_out) {
+    OWC_TRY(ensure(c, c->out_s, n * k * sizeof(float)));
+    OWC_TRY(ensure(c, c->out_i, n * k * sizeof(int32_t)));
+    ds = static_cast<float*>(c->out_s.p);
+    di = static_cast<int32_t*>(c->out_i.p);
+    if (out_paired) {
+      OWC_TRY(ensure(c, c->out_p, n * sizeof(float)));
+      dp = static_cast<float*>(c->out_p.p);
+    }
+  }
+  OWC_TRY(encode_all(e, ids, ids_space, cu, n_seq, precision, z, zb));
+  if (bf) OWC_TRY(launch_convert(c, zc, static_cast<__nv_bfloat16*>(c->zcb.p), static_cast<long long>(C) * H));
+  OWC_TRY(sim_topk_device(c, z, zb, n_seq, zc, static_cast<const __nv_bfloat16*>(c->zcb.p), C, H, k, precision,
+                          static_cast<const int32_t*>(d_targets), ds, di, (targets && out_paired) ? dp : nullptr));
+  if (host_out) {
+    OWC_TRY(from_device(c, out_scores, ds, n * k * sizeof(float), OWC_MEM_HOST));
+    OWC_TRY(from_device(c, out_idx, di, n * k * sizeof(int32_t), OWC_MEM_HOST));
+    if (targets && out_paired) OWC_TRY(from_device(c, out_paired, dp, n * sizeof(float), OWC_MEM_HOST));
+    if (out_embeds) OWC_TRY(from_device(c, out_embeds, z, n * H * sizeof(float), OWC_MEM_HOST));
+    return sync_and_check(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: kernel-level test / bench hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t owc_debug_gemm(owc_ctx* c, const float* a, const float* w, const float* bias, int32_t m, int32_t n,
+                                  int32_t kdim, int32_t precision, int32_t tile_n, float* out) {
+  if (!c || !a || !w || !out) return fail("owc_debug_gemm: NULL argument");
+  if (m <= 0 || n <= 0 || kdim <= 0) return fail("owc_debug_gemm: bad shape");
+  CU_OK(cudaSetDevice(c->device));
+  if (precision == OWC_PREC_FP32) return launch_gemm_f32<EPF_BIAS>(c, a, w, bias, nullptr, out, m, n, kdim, n);
+  OWC_TRY(ensure(c, c->tmp_a, static_cast<size_t>(m) * kdim * 2));
+  OWC_TRY(ensure(c, c->tmp_b, static_cast<size_t>(n) * kdim * 2));
+  OWC_TRY(launch_convert(c, a, static_cast<__nv_bfloat16*>(c->tmp_a.p), static_cast<long long>(m) * kdim));
+  OWC_TRY(launch_convert(c, w, static_cast<__nv_bfloat16*>(c->tmp_b.p), static_cast<long long>(n) * kdim));
+  if (tile_n == 0) tile_n = kEncBN;
+  CUtensorMap ta, tb;
+  OWC_TRY(make_tmap(c, &ta, c->tmp_a.p, m, kdim, 128));
+  OWC_TRY(make_tmap(c, &tb, c->tmp_b.p, n, kdim, tile_n));
+  GemmArgs g{};
+  g.M = m; g.N = n; g.K = kdim; g.bias = bias; g.out = out; g.ldo = n;
+  switch (tile_n) {
+    case 128: return launch_gemm_tc<128, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 128));
+    case 192: return launch_gemm_tc<192, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 192));
+    case 256: return launch_gemm_tc<256, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 256));
+    default: return fail("tile_n must be 128, 192 or 256");
+  }
+}
+
+__global__ void k_fill_unit_bf16(__nv_bfloat16* p, long long rows, int dim, unsigned seed) {
+  // pseudo-random rows with norm ~1 (bench input only)
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * dim) return;
+  unsigned x = static_cast<unsigned>(i) * 2654435761u + seed;
+  x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+  const float u = (static_cast<float>(x & 0xFFFFFF) / 8388608.0f - 1.0f);   // [-1, 1)
+  p[i] = __float2bfloat16_rn(u * 1.7320508f * rsqrtf(static_cast<float>(dim)));
+}
+
+extern "C" int32_t owc_bench_sim_kernel(owc_ctx* c, int64_t n, int32_t C, int32_t dim, int32_t k, int32_t iters,
+                                        float* ms_per_launch) {
+  if (!c || !ms_per_launch) return fail("owc_bench_sim_kernel: NULL argument");
+  if (n <= 0 || C <= 0 || dim % 64 != 0 || iters <= 0 || k < 1 || k > 16) return fail("owc_bench_sim_kernel: bad arguments");
+  CU_OK(cudaSetDevice(c->device));
+  OWC_TRY(ensure(c, c->zpb, static_cast<size_t>(n) * dim * 2));
+  OWC_TRY(ensure(c, c->zcb, static_cast<size_t>(C) * dim * 2));
+  __nv_bfloat16* zpb = static_cast<__nv_bfloat16*>(c->zpb.p);
+  __nv_bfloat16* zcb = static_cast<__nv_bfloat16*>(c->zcb.p);
+  k_fill_unit_bf16<<<static_cast<unsigned>((n * dim + 255) / 256), 256, 0, c->stream>>>(zpb, n, dim, 17u);
+  OWC_TRY(check_launch(c, "k_fill_unit_bf16"));
+  k_fill_unit_bf16<<<static_cast<unsigned>((static_cast<long long>(C) * dim + 255) / 256), 256, 0, c->stream>>>(zcb, C, dim, 91u);
+  OWC_TRY(check_launch(c, "k_fill_unit_bf16"));
+  const int KC = (k <= 5) ? 8 : 16;
+  int splits = 1;
+  auto run = [&]() -> int {
+    if (C <= 128) return KC == 8 ? sim_candidates<128, 8>(c, zpb, n, zcb, C, dim, &splits) : sim_candidates<128, 16>(c, zpb, n, zcb, C, dim, &splits);
+    return KC == 8 ? sim_candidates<256, 8>(c, zpb, n, zcb, C, dim, &splits) : sim_candidates<256, 16>(c, zpb, n, zcb, C, dim, &splits);
+  };
+  OWC_TRY(run());  // warm-up (also sizes the candidate buffers)
+  OWC_TRY(run());
+  cudaEvent_t e0, e1;
+  CU_OK(cudaEventCreate(&e0));
+  CU_OK(cudaEventCreate(&e1));
+  CU_OK(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) OWC_TRY(run());
+  CU_OK(cudaEventRecord(e1, c->stream));
+  CU_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return 0;
+}

@@ -18,21 +18,11 @@ SEED = 1234
 
 
 def build_model(arch: A.EncoderArch, seed: int = SEED):
-    """Seeded random-init HF model of ``arch`` (SURVEY.md 8c "Weight init")."""
-    from transformers import BertConfig, BertModel, MPNetConfig, MPNetModel
+    """Seeded random-init HF model of ``arch`` (SURVEY.md 8c "Weight init"); shared with the product's
+    offline weight source so both sides hold bit-identical weights."""
+    from owc_b200.weights import hf_random_init
 
-    torch.manual_seed(seed)
-    if arch.kind == A.KIND_BERT:
-        cfg = BertConfig(vocab_size=arch.vocab, hidden_size=arch.hidden, num_hidden_layers=arch.layers,
-                         num_attention_heads=arch.heads, intermediate_size=arch.inter,
-                         max_position_embeddings=arch.max_pos, type_vocab_size=arch.type_vocab,
-                         layer_norm_eps=arch.ln_eps, hidden_act="gelu")
-        return BertModel(cfg).eval()
-    cfg = MPNetConfig(vocab_size=arch.vocab, hidden_size=arch.hidden, num_hidden_layers=arch.layers,
-                      num_attention_heads=arch.heads, intermediate_size=arch.inter,
-                      max_position_embeddings=arch.max_pos, layer_norm_eps=arch.ln_eps,
-                      relative_attention_num_buckets=arch.rel_buckets)
-    return MPNetModel(cfg).eval()
+    return hf_random_init(arch, seed)
 
 
 def build_hf_tokenizer(arch: A.EncoderArch, vocab: list[str]):

@@ -1,0 +1,207 @@
+"""Host-side logic on CPU: tokenizer/packing, weight blob, synthetic data, plugin registry and the
+metric bodies driven by an oracle-backed fake engine (tests may use the oracle; the product may not)."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import owc_b200  # noqa: F401
+from oracle import encoder_ref
+from owc_b200 import arch as A
+from owc_b200 import metrics, synth
+from owc_b200 import text as T
+from owc_b200.tokenizer import HostTokenizer, pack_ids
+
+
+class OracleEngine:
+    """Stands in for owc_b200.engine.Engine in CPU tests: same methods, oracle arithmetic."""
+
+    def __init__(self, bundle):
+        self.b = bundle
+        self.arch = bundle.arch
+
+    def encode(self, ids, cu, out="host", precision=None):
+        n = len(cu) - 1
+        lens = np.diff(cu)
+        t = max(int(lens.max()) if n else 1, 1)
+        pad = self.b.arch.pad_id
+        ids_p = np.full((n, t), pad, dtype=np.int64)
+        mask = np.zeros((n, t), dtype=np.int64)
+        for i in range(n):
+            ids_p[i, :lens[i]] = ids[cu[i]:cu[i + 1]]
+            mask[i, :lens[i]] = 1
+        z = encoder_ref.encode_padded(self.b.sd, self.b.arch, torch.from_numpy(ids_p), torch.from_numpy(mask))
+        return z.numpy()
+
+    def pair_dot(self, a, b, a_index=None, b_index=None):
+        a = torch.from_numpy(np.asarray(a))
+        b = torch.from_numpy(np.asarray(b))
+        if a_index is not None:
+            a = a[torch.from_numpy(np.asarray(a_index)).long()]
+        if b_index is not None:
+            b = b[torch.from_numpy(np.asarray(b_index)).long()]
+        return encoder_ref.paired_dot(a, b).numpy()
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def oracle_backed(minilm, monkeypatch):
+    monkeypatch.setattr(T, "sentence_bert_model", OracleEngine(minilm))
+    monkeypatch.setattr(T, "sentence_bert_processor", HostTokenizer(minilm.vocab, "bert"))
+    yield minilm
+
+
+def test_vocab_is_deterministic_and_real_sized():
+    v = synth.build_vocab("bert")
+    assert len(v) == 30522 and v[0] == "[PAD]" and v[100] == "[UNK]" and v[101] == "[CLS]" and v[102] == "[SEP]"
+    assert v == synth.build_vocab("bert")
+    m = synth.build_vocab("mpnet", 30527)
+    assert m[:4] == ["<s>", "<pad>", "</s>", "<unk>"] and m[-1] == "<mask>"
+
+
+def test_real_class_lists_present():
+    assert len(synth.real_class_names("caltech101")) == 100
+    assert len(synth.real_class_names("flowers102")) == 102
+    assert len(synth.real_class_names("food101")) == 101
+    assert "apple pie" in synth.real_class_names("food101")
+
+
+def test_predictions_distinct_and_seeded():
+    words = synth.vocab_words(synth.build_vocab("bert"))
+    cls = synth.make_class_names(50, words)
+    p1, t1 = synth.make_predictions(2000, cls, words)
+    p2, t2 = synth.make_predictions(2000, cls, words)
+    assert p1 == p2 and t1 == t2 and len(set(p1)) == 2000 and len(set(cls)) == 50
+
+
+@pytest.mark.parametrize("name,kind", [("minilm", "bert"), ("mpnet", "mpnet")])
+def test_host_tokenizer_matches_hf(name, kind, request):
+    b = request.getfixturevalue(name)
+    tok = HostTokenizer(b.vocab, kind)
+    texts = [str(s) for s in b.gold["preds"]] + [str(s) for s in b.gold["class_names"]] + ["", "  ", "Ünï cödé ÀB", "x" * 150]
+    ours = tok.encode_ragged(texts)
+    theirs = b.hf_tok(texts, padding=False, truncation=True)["input_ids"]
+    assert ours == theirs
+    long = " ".join(["ab"] * 700)
+    assert len(tok.encode_ragged([long])[0]) == 512 == len(b.hf_tok([long], truncation=True)["input_ids"][0])
+
+
+def test_pack_ids_layout():
+    ids, cu = pack_ids([[1, 2, 3], [], [4]])
+    assert ids.dtype == np.int32 and cu.dtype == np.int32
+    assert ids.tolist() == [1, 2, 3, 4] and cu.tolist() == [0, 3, 3, 4]
+    ids, cu = pack_ids([])
+    assert ids.size == 0 and cu.tolist() == [0]
+
+
+@pytest.mark.parametrize("name", ["minilm", "mpnet"])
+def test_weight_blob_layout(name, request):
+    b = request.getfixturevalue(name)
+    blob = A.pack_weights(b.arch, b.sd)
+    assert blob.dtype == np.float32 and blob.size == A.blob_num_floats(b.arch)
+    h = b.arch.hidden
+    w = b.sd["embeddings.word_embeddings.weight"].numpy()
+    assert np.array_equal(blob[:w.size].reshape(w.shape), w)
+    last = b.sd[f"encoder.layer.{b.arch.layers - 1}.output.LayerNorm.bias"].numpy()
+    assert np.array_equal(blob[-h:], last)
+    bad = dict(b.sd)
+    bad["embeddings.LayerNorm.weight"] = torch.zeros(h + 1)
+    with pytest.raises(ValueError):
+        A.pack_weights(b.arch, bad)
+
+
+def test_mpnet_lut_matches_table(mpnet):
+    b = mpnet
+    blob = A.pack_weights(b.arch, b.sd)
+    h, p = b.arch.hidden, b.arch.max_pos
+    off = b.arch.vocab * h + p * h + 2 * h
+    lut = blob[off:off + b.arch.heads * (2 * p - 1)].reshape(b.arch.heads, 2 * p - 1)
+    table = b.sd["encoder.relative_attention_bias.weight"]
+    rel = torch.arange(-(p - 1), p)
+    want = table[encoder_ref.mpnet_bucket(rel)].T.numpy()
+    assert np.array_equal(lut, want)
+
+
+def test_registry_surface():
+    for name in ("semantic_similarity", "mean_average_semantic_similarity", "concept_semantic_similarity"):
+        info = metrics.get_metric_info(name)
+        assert info.name == name and info.higher_is_better is True and info.output_types == ["generate_until"]
+        assert info.group_fn is metrics.get_aggregation_builder(name)
+        items = [("a", ["b"])]
+        assert info.builder_fn(items) is items          # pass-through (_instance.py:445-462)
+    with pytest.raises(KeyError):
+        metrics.get_metric_info("nope")
+
+
+def test_reduce_validation_raises_before_any_work():
+    for fn in ("semantic_similarity", "mean_average_semantic_similarity", "concept_semantic_similarity"):
+        with pytest.raises(ValueError):
+            metrics.get_aggregation_builder(fn)([("a", ["b"])], reduce="sum")
+
+
+def test_operator_contract(oracle_backed):
+    b = oracle_backed
+    batch = {"text": ["accordion", "a photo of a cat"]}
+    out = T.encode_sentence_bert(batch, input_column="text")
+    assert out is batch and "text_sentence_bert_embeds" in batch
+    e = batch["text_sentence_bert_embeds"]
+    assert isinstance(e, list) and isinstance(e[0], list) and isinstance(e[0][0], float) and len(e[0]) == 384
+    with pytest.raises(ValueError):
+        T.encode_sentence_bert({"other": ["x"]}, input_column="text")
+    with pytest.raises(NotImplementedError):
+        T.encode_sentence_bert({"text": "not a list"}, input_column="text")
+    out = T.encode_sentence_bert({"p": ["x"]}, input_column="p", output_column="z")
+    assert "z" in out
+    gold = b.gold["class_embeds"][3]
+    assert np.abs(np.asarray(e[0]) - gold).max() < 2e-6        # "accordion" is Caltech101 class 3
+
+
+def test_metric_bodies_match_reference_goldens(oracle_backed):
+    b = oracle_backed
+    cls = [str(s) for s in b.gold["class_names"]]
+    preds = [str(s) for s in b.gold["preds"]]
+    items = [(cls[t], [p]) for t, p in zip(b.gold["targets"], preds)]
+    ss = metrics.get_metric_info("semantic_similarity")
+    got = ss.group_fn(ss.builder_fn(items), reduce="none")
+    assert isinstance(got, list) and isinstance(got[0], float)
+    assert np.abs(np.asarray(got, np.float32) - b.gold["paired_scores"]).max() < 2e-6
+    assert abs(ss.group_fn(items) - float(b.gold["paired_mean"])) < 1e-6
+    # online item shape [[gold], [resp...]] and multi-response "last wins" (_group.py:518-519)
+    online = [[[cls[t]], ["ignored", p]] for t, p in zip(b.gold["targets"][:16], preds[:16])]
+    got2 = ss.group_fn(online, reduce="none")
+    assert np.abs(np.asarray(got2, np.float32) - b.gold["paired_scores"][:16]).max() < 2e-6
+
+    mass = metrics.get_aggregation_builder("mean_average_semantic_similarity")
+    none = mass(items, reduce="none")
+    assert list(none) == [str(k) for k in b.gold["mass_keys"]]
+    arr = np.asarray([none[k] for k in none], np.float32)
+    assert np.array_equal(arr[:5], b.gold["mass_none"][:5]) and np.abs(arr[5] - b.gold["mass_none"][5]).max() < 1e-6
+    assert all(isinstance(v, int) for v in none["semantic_similarity@0.5"][:4])
+    mean = mass(items, reduce="mean")
+    assert np.abs(np.asarray(list(mean.values())) - b.gold["mass_mean"]).max() < 1e-6
+
+
+def test_concept_metric_matches_reference_golden(oracle_backed, monkeypatch):
+    from oracle import metrics_ref
+
+    b = oracle_backed
+    monkeypatch.setattr(T, "concept_extractor", metrics_ref.simple_concepts)
+    cls = [str(s) for s in b.gold["class_names"]]
+    cpreds = [str(s) for s in b.gold["concept_preds"]]
+    items = [(cls[t], [p]) for t, p in zip(b.gold["targets"][:len(cpreds)], cpreds)]
+    fn = metrics.get_aggregation_builder("concept_semantic_similarity")
+    rows = fn(items, reduce="none")
+    gold = json.loads(str(b.gold["concept_json"]))
+    for (c, s), (gc, gs) in zip(rows, gold, strict=True):
+        assert list(c) == gc and np.abs(np.asarray(s) - np.asarray(gs)).max() < 2e-6
+    for red in ("max", "mean", "median", "min"):
+        assert abs(fn(items, reduce=red) - float(b.gold[f"concept_{red}"])) < 1e-6
+
+
+def test_encode_unique_dedups(oracle_backed):
+    z, inv = T.encode_unique(["a b", "c", "a b", "c", "d"])
+    assert z.shape == (3, 384) and inv.tolist() == [0, 1, 0, 1, 2]
