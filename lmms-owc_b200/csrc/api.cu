@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/owc_b200.h"
+#include "attn_mma.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -481,6 +482,34 @@ static int launch_attn(owc_encoder* e, const AttnArgs& aa) {
   return check_launch(c, "k_attn");
 }
 
+// bf16 production path for sequences of at most 64 tokens: tensor-core attention, CTA per sequence.
+static int launch_attn_mma(owc_encoder* e, const AttnArgs& aa) {
+  owc_ctx* c = e->ctx;
+  const int D = e->arch.hidden / e->arch.heads;
+  ProfScope prof(c, OWC_KCAT_ATTN);
+#define ATTN_MMA_LAUNCH(DD, TP)                                                                             \
+  do {                                                                                                      \
+    using Cfg = AttnMmaCfg<DD, TP>;                                                                         \
+    static bool attr_done = false;                                                                          \
+    if (Cfg::SMEM_BYTES > 48 * 1024 && !attr_done) {                                                        \
+      CU_OK(cudaFuncSetAttribute(k_attn_mma<DD, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); \
+      attr_done = true;                                                                                     \
+    }                                                                                                       \
+    k_attn_mma<DD, TP><<<aa.n_seq, 128, Cfg::SMEM_BYTES, c->stream>>>(aa);                                  \
+  } while (0)
+  if (D == 32) {
+    if (aa.max_t <= 16) ATTN_MMA_LAUNCH(32, 16);
+    else if (aa.max_t <= 32) ATTN_MMA_LAUNCH(32, 32);
+    else ATTN_MMA_LAUNCH(32, 64);
+  } else {
+    if (aa.max_t <= 16) ATTN_MMA_LAUNCH(64, 16);
+    else if (aa.max_t <= 32) ATTN_MMA_LAUNCH(64, 32);
+    else ATTN_MMA_LAUNCH(64, 64);
+  }
+#undef ATTN_MMA_LAUNCH
+  return check_launch(c, "k_attn_mma");
+}
+
 static int ensure_f32_workspace(owc_encoder* e) {
   if (e->qkv32) return 0;
   const size_t cap = e->cap, h = e->arch.hidden, I = e->arch.inter;
@@ -524,7 +553,8 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
       g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = e->qkv; g.ldo = 3 * H;
       OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, e->tm_xb, L.tm_wqkv, g, pick_splits(c, M, g.N, kEncBN))));
       aa.qkv = e->qkv; aa.out = e->ao;
-      OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
+      if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
+      else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
       g = GemmArgs{};
       g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = e->x; g.out = e->y; g.ldo = H;
       OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, g, pick_splits(c, M, g.N, kEncBN))));
@@ -665,19 +695,20 @@ static int sim_candidates(owc_ctx* c, const __nv_bfloat16* zpb, long long n, con
   OWC_TRY(make_tmap(c, &ta, zpb, static_cast<uint64_t>(n), dim, 128));
   OWC_TRY(make_tmap(c, &tb, zcb, static_cast<uint64_t>(C), dim, BN));
   int splits = pick_splits(c, static_cast<int>(n), C, BN);
-  splits = std::min(splits, 128 / KC);
+  splits = std::min(splits, 64 / KC);   // 2 lists per split (chunk parity); re-score handles <= 128 candidates/row
   const int tiles = (C + BN - 1) / BN;
   splits = std::max(1, std::min(splits, tiles));
   const int tpc = (tiles + splits - 1) / splits;
   splits = (tiles + tpc - 1) / tpc;
-  OWC_TRY(ensure(c, c->cand_s, static_cast<size_t>(splits) * n * KC * sizeof(float)));
-  OWC_TRY(ensure(c, c->cand_i, static_cast<size_t>(splits) * n * KC * sizeof(int)));
+  const size_t lists = 2 * static_cast<size_t>(splits);
+  OWC_TRY(ensure(c, c->cand_s, lists * n * KC * sizeof(float)));
+  OWC_TRY(ensure(c, c->cand_i, lists * n * KC * sizeof(int)));
   GemmArgs g{};
   g.M = static_cast<int>(n); g.N = C; g.K = dim;
   g.cand_score = static_cast<float*>(c->cand_s.p);
   g.cand_idx = static_cast<int*>(c->cand_i.p);
   OWC_TRY((launch_gemm_tc<BN, EPI_TOPK, KC>(c, ta, tb, g, splits)));
-  *splits_out = splits;
+  *splits_out = static_cast<int>(lists);   // candidate lists per row
   return 0;
 }
 

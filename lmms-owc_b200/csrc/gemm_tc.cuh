@@ -9,8 +9,9 @@
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (128 x BN x 16) per stage into one of TWO TMEM
 //                      accumulator buffers; tcgen05.commit frees the stage and, after the last
 //                      k-block, publishes the accumulator on `tfull[buf]`
-//   warps 2-5          epilogue: thread r of TMEM lane quadrant (warp & 3) owns output row r;
-//                      tcgen05.ld 32 columns at a time; fused bias / erf-GELU / residual add, or
+//   warps 2-9          epilogue: thread r of TMEM lane quadrant (warp & 3) owns output row r, the two
+//                      warps of a quadrant take alternate 32-column chunks (tcgen05.ld, software-
+//                      pipelined); fused bias / erf-GELU / residual add, or
 //                      the per-row top-k candidate list kept in registers across the whole class
 //                      sweep (the similarity matrix never leaves the SM)
 // The two accumulator buffers let the epilogue of tile t overlap the MMAs of tile t+1.
@@ -35,7 +36,7 @@ struct GemmArgs {
   const float* residual;   // [M, ldo] fp32 (EPI_BIAS_RES_F32)
   void* out;               // bf16 or fp32 [M, ldo]
   int ldo;
-  float* cand_score;       // EPI_TOPK: [gridDim.y, M, KC]
+  float* cand_score;       // EPI_TOPK: [2 * gridDim.y, M, KC] (two chunk parities per column split)
   int* cand_idx;
 };
 
@@ -48,8 +49,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int THREADS = 192;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
 
 template <int KC>
@@ -84,12 +86,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer arithmetic on the __shared__ array itself so accesses stay in the shared window
+  // (LDS/STS) instead of degrading to generic loads; SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_smem = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,7 +108,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], Cfg::EPI_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -161,26 +166,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ---------------- epilogue (warps 2..9): two warps per TMEM lane quadrant ----------------
+    // Warp w may only touch TMEM lanes [32*(w&3), +32); the two warps of a quadrant take alternate
+    // 32-column chunks, so one warp's tcgen05.ld latency hides behind the other's math and stores.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;   // 0 | 1
     const int row = m_blk * BM + q * 32 + lane;
     const bool row_ok = row < g.M;
     TopK<KC> top;
     if constexpr (EPI == EPI_TOPK) top.init();
+    const int et = threadIdx.x - 64;    // 0..255 within the epilogue group
+    constexpr int NC = BN / 32;         // chunks per tile
+    constexpr int NCW = NC / 2;         // chunks per warp
     int t = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++t) {
       const int buf = t & 1;
       const uint32_t use = static_cast<uint32_t>(t >> 1);
+      float* bias_s = bias_smem + buf * BN;
+      if constexpr (EPI != EPI_TOPK) {
+        // stage this tile's bias slice in shared memory while the MMAs of the tile are still running
+        for (int i = et; i < BN; i += Cfg::EPI_THREADS) {
+          const int n = tile * BN + i;
+          bias_s[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.f;
+        }
+        named_bar_sync(1, Cfg::EPI_THREADS);
+      }
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      if constexpr (EPI == EPI_TOPK) {
+        // code kept small on purpose (32 inlined offers): the sweep runs hundreds of tiles
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = tile * BN + c * 32;
-        if (n0 >= g.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c * 32), v);
-        tmem_ld_wait();
-        if constexpr (EPI == EPI_TOPK) {
+        for (int cw = 0; cw < NCW; ++cw) {
+          const int c = 2 * cw + half;
+          const int n0 = tile * BN + c * 32;
+          if (n0 >= g.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait_dep(v);
           if (n0 + 32 <= g.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) top.offer(__uint_as_float(v[j]), n0 + j);
@@ -189,27 +212,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int j = 0; j < 32; ++j)
               if (n0 + j < g.N) top.offer(__uint_as_float(v[j]), n0 + j);
           }
-        } else if (row_ok) {
+        }
+      } else {
+        uint32_t v[2][32];
+        tmem_ld_32x32(tbase + static_cast<uint32_t>(half * 32), v[0]);
+#pragma unroll
+        for (int cw = 0; cw < NCW; ++cw) {
+          const int c = 2 * cw + half;
+          const int n0 = tile * BN + c * 32;
+          tmem_ld_wait_dep(v[cw & 1]);
+          if (cw + 1 < NCW) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 2) * 32), v[(cw + 1) & 1]);  // overlaps the math below
+          if (n0 >= g.N || !row_ok) continue;
+          const uint32_t (&vc)[32] = v[cw & 1];
           float f[32];
-          if (g.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            f[4 * j + 0] = __uint_as_float(vc[4 * j + 0]) + b.x;
+            f[4 * j + 1] = __uint_as_float(vc[4 * j + 1]) + b.y;
+            f[4 * j + 2] = __uint_as_float(vc[4 * j + 2]) + b.z;
+            f[4 * j + 3] = __uint_as_float(vc[4 * j + 3]) + b.w;
           }
           const size_t off = static_cast<size_t>(row) * g.ldo + n0;
           if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
             if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
             }
             uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + off);
 #pragma unroll
@@ -242,7 +271,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     if constexpr (EPI == EPI_TOPK) {
       if (row_ok) {
-        const size_t base = (static_cast<size_t>(blockIdx.y) * g.M + row) * KC;
+        // each (column split, chunk parity) pair contributes its own candidate list
+        const size_t base = (static_cast<size_t>(blockIdx.y * 2 + half) * g.M + row) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) { g.cand_score[base + i] = top.s[i]; g.cand_idx[base + i] = top.id[i]; }
       }
