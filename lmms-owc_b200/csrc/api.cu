@@ -62,6 +62,7 @@ struct owc_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int chunk_tokens = 0;
+  int gemm_mode = 2;   // 0: 1-CTA tcgen05, 1: CTA pairs, 2: CTA pairs + resident A (env OWC_GEMM_MODE)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -78,7 +79,8 @@ struct LayerW {
   const float *bqkv, *bo, *ln1g, *ln1b, *b1, *b2, *ln2g, *ln2b;   // fp32 (device)
   const float *wqkv32, *wo32, *w132, *w232;                        // fp32 masters (check mode)
   const __nv_bfloat16 *wqkv, *wo, *w1, *w2;                        // bf16 operand copies
-  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;          // W maps, box = kEncBN rows (1-CTA kernel)
+  CUtensorMap tm2_wqkv, tm2_wo, tm2_w1, tm2_w2;      // W maps, box = kEncBN/2 rows (CTA-pair kernel)
 };
 
 struct owc_encoder {
@@ -92,7 +94,8 @@ struct owc_encoder {
   float *x = nullptr, *y = nullptr;
   __nv_bfloat16 *xb = nullptr, *qkv = nullptr, *ao = nullptr, *f = nullptr;
   float *qkv32 = nullptr, *ao32 = nullptr, *f32 = nullptr;   // check mode, allocated on first use
-  CUtensorMap tm_xb, tm_ao, tm_f;
+  CUtensorMap tm_xb, tm_ao, tm_f;            // A-operand maps (box 128 rows x 64)
+  CUtensorMap tmo_qkv, tmo_f, tmo_y;         // epilogue TMA-store maps (box 32 x 32)
 };
 
 constexpr int kEncBN = 192;   // divides 3H, H and I of both architectures (1152/384/1536, 2304/768/3072)
@@ -176,24 +179,73 @@ static int make_tmap(owc_ctx* c, CUtensorMap* m, const void* base, uint64_t rows
   return 0;
 }
 
+// Output matrix [rows, cols] (bf16 or fp32, row-major) -> tensor map for the epilogue's TMA stores:
+// box = 32 x 32 elements; bf16 rows are 64 B (SWIZZLE_64B), fp32 rows 128 B (SWIZZLE_128B), matching
+// the staging layout written by stage_chunk() in gemm_tc.cuh.
+static int make_out_tmap(owc_ctx* c, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, bool is_bf16) {
+  const uint64_t esz = is_bf16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("output tensor map base not 16-byte aligned");
+  if ((cols * esz) % 16 != 0) return fail("output row pitch (%llu B) is not a multiple of 16", (unsigned long long)(cols * esz));
+  if (rows == 0) rows = 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * esz};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                               const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               is_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (output) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+static int check_gemm_shape(const GemmArgs& g, int epi) {
+  if (g.K % 64 != 0 || g.K <= 0) return fail("tcgen05 GEMM needs K %% 64 == 0 (K=%d)", g.K);
+  if (epi == EPI_BIAS_RES_F32 && g.N % 32 != 0) return fail("residual epilogue needs N %% 32 == 0 (N=%d)", g.N);
+  return 0;
+}
+
 template <int BN, int EPI, int KC>
-static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs g, int splits) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
+                          int splits) {
+  using Cfg = GemmCfg<BN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
     CU_OK(cudaFuncSetAttribute(k_gemm_tc<BN, EPI, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  if (g.K % 64 != 0 || g.K <= 0) return fail("tcgen05 GEMM needs K %% 64 == 0 (K=%d)", g.K);
-  if (EPI != EPI_TOPK && g.N % 32 != 0) return fail("tcgen05 GEMM needs N %% 32 == 0 (N=%d)", g.N);
+  OWC_TRY(check_gemm_shape(g, EPI));
   const int tiles = (g.N + BN - 1) / BN;
   splits = std::max(1, std::min(splits, tiles));
   g.tiles_per_cta = (tiles + splits - 1) / splits;
   const int gy = (tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
   dim3 grid((g.M + 127) / 128, gy);
   ProfScope prof(c, EPI == EPI_TOPK ? OWC_KCAT_SIM : OWC_KCAT_GEMM);
-  k_gemm_tc<BN, EPI, KC><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, g);
+  k_gemm_tc<BN, EPI, KC><<<grid, kGemmThreads, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, tc, g);
   return check_launch(c, "k_gemm_tc");
+}
+
+// CTA-pair kernel: `tb_half` is the W tensor map with a BN/2-row box (each CTA stages half a tile).
+template <int BN, int EPI, int KC, bool ARES>
+static int launch_gemm_tc2(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, GemmArgs g,
+                           int splits) {
+  using Cfg = Gemm2Cfg<BN, EPI, ARES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_OK(cudaFuncSetAttribute(k_gemm_tc2<BN, EPI, KC, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  OWC_TRY(check_gemm_shape(g, EPI));
+  if (ARES && g.K > kAresMaxK) return fail("resident-A GEMM needs K <= %d (K=%d)", kAresMaxK, g.K);
+  const int tiles = (g.N + BN - 1) / BN;
+  splits = std::max(1, std::min(splits, tiles));
+  g.tiles_per_cta = (tiles + splits - 1) / splits;
+  const int gy = (tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  const int pairs = (g.M + 255) / 256;
+  dim3 grid(2 * pairs, gy);   // the odd tail CTA of a pair only sees out-of-range rows (TMA zero-fills / clips)
+  ProfScope prof(c, EPI == EPI_TOPK ? OWC_KCAT_SIM : OWC_KCAT_GEMM);
+  k_gemm_tc2<BN, EPI, KC, ARES><<<grid, kGemmThreads, Cfg::SMEM_BYTES, c->stream>>>(ta, tb_half, tc, g);
+  return check_launch(c, "k_gemm_tc2");
 }
 
 // column splits so that (row blocks x splits) covers the SMs when there are few row blocks
@@ -201,6 +253,17 @@ static int pick_splits(const owc_ctx* c, int m, int n, int bn) {
   const int mb = (m + 127) / 128, tiles = (n + bn - 1) / bn;
   if (mb >= c->sm_count) return 1;
   return std::max(1, std::min(tiles, (c->sm_count + mb - 1) / mb));
+}
+
+// Mode-dispatched contraction. gemm_mode: 0 = one CTA per 128 rows; 1 = CTA pairs (cta_group::2);
+// 2 = CTA pairs with the A block resident in shared memory whenever K <= 384 (default).
+template <int BN, int EPI, int KC>
+static int launch_gemm(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb_full, const CUtensorMap& tb_half,
+                       const CUtensorMap& tc, const GemmArgs& g) {
+  const int splits = pick_splits(c, g.M, g.N, BN);
+  if (c->gemm_mode == 0) return launch_gemm_tc<BN, EPI, KC>(c, ta, tb_full, tc, g, splits);
+  if (c->gemm_mode == 2 && g.K <= kAresMaxK) return launch_gemm_tc2<BN, EPI, KC, true>(c, ta, tb_half, tc, g, splits);
+  return launch_gemm_tc2<BN, EPI, KC, false>(c, ta, tb_half, tc, g, splits);
 }
 
 template <int EPF>
@@ -253,6 +316,7 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (!c) return fail("out of host memory");
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* gm = getenv("OWC_GEMM_MODE")) c->gemm_mode = std::max(0, std::min(2, atoi(gm)));
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -424,6 +488,8 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
         launch_convert(c, L.w232, const_cast<__nv_bfloat16*>(L.w2), h * I)) { owc_encoder_destroy(e); return 1; }
     if (make_tmap(c, &L.tm_wqkv, L.wqkv, 3 * h, h, kEncBN) || make_tmap(c, &L.tm_wo, L.wo, h, h, kEncBN) ||
         make_tmap(c, &L.tm_w1, L.w1, I, h, kEncBN) || make_tmap(c, &L.tm_w2, L.w2, h, I, kEncBN)) { owc_encoder_destroy(e); return 1; }
+    if (make_tmap(c, &L.tm2_wqkv, L.wqkv, 3 * h, h, kEncBN / 2) || make_tmap(c, &L.tm2_wo, L.wo, h, h, kEncBN / 2) ||
+        make_tmap(c, &L.tm2_w1, L.w1, I, h, kEncBN / 2) || make_tmap(c, &L.tm2_w2, L.w2, h, I, kEncBN / 2)) { owc_encoder_destroy(e); return 1; }
   }
   if (static_cast<size_t>(p - e->w32) != n_floats) LOAD_FAIL("internal: blob walk mismatch");
 
@@ -440,6 +506,8 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   LOAD_CU(cudaMemsetAsync(e->f, 0, cap * I * sizeof(__nv_bfloat16), c->stream));
   if (make_tmap(c, &e->tm_xb, e->xb, cap, h, 128) || make_tmap(c, &e->tm_ao, e->ao, cap, h, 128) ||
       make_tmap(c, &e->tm_f, e->f, cap, I, 128)) { owc_encoder_destroy(e); return 1; }
+  if (make_out_tmap(c, &e->tmo_qkv, e->qkv, cap, 3 * h, true) || make_out_tmap(c, &e->tmo_f, e->f, cap, I, true) ||
+      make_out_tmap(c, &e->tmo_y, e->y, cap, h, false)) { owc_encoder_destroy(e); return 1; }
   LOAD_CU(cudaStreamSynchronize(c->stream));  // `weights` may be freed by the caller after return
 #undef LOAD_CU
 #undef LOAD_FAIL
@@ -550,14 +618,14 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
     const LayerW& L = e->layers[l];
     if (bf) {
       GemmArgs g{};
-      g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = e->qkv; g.ldo = 3 * H;
-      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, e->tm_xb, L.tm_wqkv, g, pick_splits(c, M, g.N, kEncBN))));
+      g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
+      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_BF16, 1>(c, e->tm_xb, L.tm_wqkv, L.tm2_wqkv, e->tmo_qkv, g)));
       aa.qkv = e->qkv; aa.out = e->ao;
       if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
       else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
       g = GemmArgs{};
-      g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = e->x; g.out = e->y; g.ldo = H;
-      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, g, pick_splits(c, M, g.N, kEncBN))));
+      g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = e->x; g.ldo = H;
+      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, L.tm2_wo, e->tmo_y, g)));
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS>(c, e->x, L.wqkv32, L.bqkv, nullptr, e->qkv32, M, 3 * H, H, 3 * H));
       aa.qkv = e->qkv32; aa.out = e->ao32;
@@ -571,11 +639,11 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
     OWC_TRY(check_launch(c, "k_ln"));
     if (bf) {
       GemmArgs g{};
-      g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = e->f; g.ldo = I;
-      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, e->tm_xb, L.tm_w1, g, pick_splits(c, M, g.N, kEncBN))));
+      g.M = M; g.N = I; g.K = H; g.bias = L.b1;
+      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, e->tm_xb, L.tm_w1, L.tm2_w1, e->tmo_f, g)));
       g = GemmArgs{};
-      g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = e->x; g.out = e->y; g.ldo = H;
-      OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, g, pick_splits(c, M, g.N, kEncBN))));
+      g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = e->x; g.ldo = H;
+      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, L.tm2_w2, e->tmo_y, g)));
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS_GELU>(c, e->x, L.w132, L.b1, nullptr, e->f32, M, I, H, I));
       OWC_TRY(launch_gemm_f32<EPF_BIAS_RES>(c, e->f32, L.w232, L.b2, e->x, e->y, M, H, I, H));
@@ -691,9 +759,11 @@ extern "C" int32_t owc_pair_dot(owc_ctx* c, const float* a, int64_t na, const in
 template <int BN, int KC>
 static int sim_candidates(owc_ctx* c, const __nv_bfloat16* zpb, long long n, const __nv_bfloat16* zcb, int C, int dim,
                           int* splits_out) {
+  const bool pair = c->gemm_mode != 0;
+  const bool ares = c->gemm_mode == 2 && dim <= kAresMaxK;
   CUtensorMap ta, tb;
   OWC_TRY(make_tmap(c, &ta, zpb, static_cast<uint64_t>(n), dim, 128));
-  OWC_TRY(make_tmap(c, &tb, zcb, static_cast<uint64_t>(C), dim, BN));
+  OWC_TRY(make_tmap(c, &tb, zcb, static_cast<uint64_t>(C), dim, pair ? BN / 2 : BN));
   int splits = pick_splits(c, static_cast<int>(n), C, BN);
   splits = std::min(splits, 64 / KC);   // 2 lists per split (chunk parity); re-score handles <= 128 candidates/row
   const int tiles = (C + BN - 1) / BN;
@@ -707,7 +777,9 @@ static int sim_candidates(owc_ctx* c, const __nv_bfloat16* zpb, long long n, con
   g.M = static_cast<int>(n); g.N = C; g.K = dim;
   g.cand_score = static_cast<float*>(c->cand_s.p);
   g.cand_idx = static_cast<int*>(c->cand_i.p);
-  OWC_TRY((launch_gemm_tc<BN, EPI_TOPK, KC>(c, ta, tb, g, splits)));
+  if (!pair) OWC_TRY((launch_gemm_tc<BN, EPI_TOPK, KC>(c, ta, tb, ta, g, splits)));   // no output map: the epilogue keeps candidates
+  else if (ares) OWC_TRY((launch_gemm_tc2<BN, EPI_TOPK, KC, true>(c, ta, tb, ta, g, splits)));
+  else OWC_TRY((launch_gemm_tc2<BN, EPI_TOPK, KC, false>(c, ta, tb, ta, g, splits)));
   *splits_out = static_cast<int>(lists);   // candidate lists per row
   return 0;
 }
@@ -860,18 +932,29 @@ extern "C" int32_t owc_debug_gemm(owc_ctx* c, const float* a, const float* w, co
   OWC_TRY(ensure(c, c->tmp_b, static_cast<size_t>(n) * kdim * 2));
   OWC_TRY(launch_convert(c, a, static_cast<__nv_bfloat16*>(c->tmp_a.p), static_cast<long long>(m) * kdim));
   OWC_TRY(launch_convert(c, w, static_cast<__nv_bfloat16*>(c->tmp_b.p), static_cast<long long>(n) * kdim));
-  if (tile_n == 0) tile_n = kEncBN;
+  if (tile_n == 0) tile_n = kEncBN + 1000 * c->gemm_mode;
+  const int variant = tile_n / 1000;   // 0: 1-CTA, 1: CTA pair, 2: CTA pair + resident A
+  const int bn = tile_n % 1000;
+  if (variant == 2 && kdim > 384) return fail("resident-A variant needs kdim <= 384");
   CUtensorMap ta, tb;
   OWC_TRY(make_tmap(c, &ta, c->tmp_a.p, m, kdim, 128));
-  OWC_TRY(make_tmap(c, &tb, c->tmp_b.p, n, kdim, tile_n));
+  OWC_TRY(make_tmap(c, &tb, c->tmp_b.p, n, kdim, variant == 0 ? bn : bn / 2));
   GemmArgs g{};
-  g.M = m; g.N = n; g.K = kdim; g.bias = bias; g.out = out; g.ldo = n;
-  switch (tile_n) {
-    case 128: return launch_gemm_tc<128, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 128));
-    case 192: return launch_gemm_tc<192, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 192));
-    case 256: return launch_gemm_tc<256, EPI_BIAS_F32, 1>(c, ta, tb, g, pick_splits(c, m, n, 256));
-    default: return fail("tile_n must be 128, 192 or 256");
+  g.M = m; g.N = n; g.K = kdim; g.bias = bias;
+  CUtensorMap tc;
+  OWC_TRY(make_out_tmap(c, &tc, out, m, n, false));
+#define DBG_CASE(BNV)                                                                                     \
+  case BNV:                                                                                               \
+    if (variant == 0) return launch_gemm_tc<BNV, EPI_BIAS_F32, 1>(c, ta, tb, tc, g, pick_splits(c, m, n, BNV));          \
+    if (variant == 1) return launch_gemm_tc2<BNV, EPI_BIAS_F32, 1, false>(c, ta, tb, tc, g, pick_splits(c, m, n, BNV));  \
+    return launch_gemm_tc2<BNV, EPI_BIAS_F32, 1, true>(c, ta, tb, tc, g, pick_splits(c, m, n, BNV));
+  switch (bn) {
+    DBG_CASE(128)
+    DBG_CASE(192)
+    DBG_CASE(256)
+    default: return fail("tile_n must be 128, 192 or 256 (+1000: CTA pair, +2000: CTA pair with resident A)");
   }
+#undef DBG_CASE
 }
 
 __global__ void k_fill_unit_bf16(__nv_bfloat16* p, long long rows, int dim, unsigned seed) {

@@ -1,20 +1,28 @@
-// gemm_tc.cuh - the tcgen05 / TMEM / TMA contraction kernel of the scoring path.
+// gemm_tc.cuh - the tcgen05 / TMEM / TMA contraction kernels of the scoring path.
 //
 //   C[M, N] = A[M, K] . W[N, K]^T        A, W bf16, K-major (row-major with K innermost)
 //
-// One kernel skeleton serves every dense contraction on the path:
-// a CTA owns one 128-row block of A and sweeps a range of BN-wide column tiles of W. Roles:
-//   warp 0 (one lane)  TMA producer: per k-block of 64, one 128x64 A box + one BNx64 W box into a
+// One skeleton serves every dense contraction on the path: a CTA owns
+// one 128-row block of A and sweeps a range of BN-wide column tiles of W. Roles:
+//   warp 0 (one lane)  TMA producer: per k-block of 64, a 128x64 A box and a W box into a
 //                      SWIZZLE_128B stage ring, completion on `full[stage]` (expect_tx)
-//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (128 x BN x 16) per stage into one of TWO TMEM
+//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (K=16 each) per stage into one of TWO TMEM
 //                      accumulator buffers; tcgen05.commit frees the stage and, after the last
 //                      k-block, publishes the accumulator on `tfull[buf]`
 //   warps 2-9          epilogue: thread r of TMEM lane quadrant (warp & 3) owns output row r, the two
 //                      warps of a quadrant take alternate 32-column chunks (tcgen05.ld, software-
-//                      pipelined); fused bias / erf-GELU / residual add, or
-//                      the per-row top-k candidate list kept in registers across the whole class
+//                      pipelined); fused bias / erf-GELU / residual add, results staged in swizzled
+//                      shared memory and written with TMA stores (a row-per-thread global store
+//                      costs 32 LSU wavefronts per instruction and bounded the first version);
+//                      or the per-row top-k candidate list kept in registers across the whole class
 //                      sweep (the similarity matrix never leaves the SM)
 // The two accumulator buffers let the epilogue of tile t overlap the MMAs of tile t+1.
+//
+// Two kernels share the epilogue:
+//   k_gemm_tc   one CTA per 128 rows (cta_group::1)
+//   k_gemm_tc2  a CTA PAIR per 256 rows (cluster of 2, cta_group::2, UMMA M=256): each CTA stages
+//               only HALF of every W tile and the pair's tensor cores read both halves. With ARES the
+//               CTA's whole A block (K <= 384) stays resident in shared memory for the sweep.
 #pragma once
 
 #include "common.cuh"
@@ -30,29 +38,60 @@ enum : int {
 };
 
 struct GemmArgs {
-  int M, N, K;             // K % 64 == 0; N % 32 == 0 unless EPI_TOPK
+  int M, N, K;             // K % 64 == 0
   int tiles_per_cta;       // column tiles swept by one CTA (gridDim.y = ceil(tiles / tiles_per_cta))
   const float* bias;       // [N] or nullptr
   const float* residual;   // [M, ldo] fp32 (EPI_BIAS_RES_F32)
-  void* out;               // bf16 or fp32 [M, ldo]
-  int ldo;
+  int ldo;                 // leading dimension of `residual`
   float* cand_score;       // EPI_TOPK: [2 * gridDim.y, M, KC] (two chunk parities per column split)
   int* cand_idx;
 };
 
-template <int BN>
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kEpiThreads;
+constexpr int kSmemLimit = 232448;   // 227 KB of dynamic shared memory per CTA
+
+// bytes of one per-warp output staging buffer: 32 rows x 32 columns
+__host__ __device__ constexpr int epi_stage_bytes(int epi) {
+  return epi == EPI_TOPK ? 0 : ((epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) ? 32 * 64 : 32 * 128);
+}
+__host__ __device__ constexpr int epi_fixed_bytes(int bn, int epi) {
+  return 1024 /*align slack*/ + 256 /*barriers*/ + 2 * bn * 4 /*bias*/ + kEpiWarps * 2 * epi_stage_bytes(epi);
+}
+__host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
+
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI)) / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
-  static constexpr int THREADS = 64 + EPI_THREADS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
+  static constexpr int STG_BYTES = epi_stage_bytes(EPI);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
+
+// CTA-pair kernel: per CTA a stage holds (optionally) a 128x64 A box and HALF a W tile (BN/2 rows).
+template <int BN, int EPI, bool ARES>
+struct Gemm2Cfg {
+  static constexpr int BM = 128;          // rows per CTA (256 per pair)
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int BH_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = (ARES ? 0 : A_BYTES) + BH_BYTES;
+  static constexpr int MAX_KB = 6;        // resident A block: K <= 384
+  static constexpr int ARES_BYTES = ARES ? MAX_KB * A_BYTES : 0;
+  static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI) - ARES_BYTES) / STAGE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int STG_BYTES = epi_stage_bytes(EPI);
+  static constexpr int SMEM_BYTES = ARES_BYTES + STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
+  static_assert(STAGES >= 3, "pipeline too shallow");
+};
+constexpr int kAresMaxK = 384;
 
 template <int KC>
 struct TopK {
@@ -62,39 +101,197 @@ struct TopK {
 #pragma unroll
     for (int i = 0; i < KC; ++i) { s[i] = -INFINITY; id[i] = -1; }
   }
-  // Keeps s[] descending; a value equal to an entry goes after it, so with columns visited in
-  // increasing order ties resolve to the lower class index.
-  __device__ __forceinline__ void offer(float v, int col) {
-    if (v > s[KC - 1]) {
-      float cv = v;
-      int ci = col;
+  // Keeps s[] descending; a value equal to an entry goes after it (stable), so equal scores keep the
+  // order in which they are inserted. Caller guarantees v > s[KC-1].
+  __device__ __forceinline__ void insert(float v, int col) {
+    float cv = v;
+    int ci = col;
 #pragma unroll
-      for (int i = 0; i < KC; ++i) {
-        const bool gt = cv > s[i];
-        const float ts = s[i];
-        const int ti = id[i];
-        if (gt) { s[i] = cv; id[i] = ci; cv = ts; ci = ti; }
-      }
+    for (int i = 0; i < KC; ++i) {
+      const bool gt = cv > s[i];
+      const float ts = s[i];
+      const int ti = id[i];
+      if (gt) { s[i] = cv; id[i] = ci; cv = ts; ci = ti; }
     }
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// shared epilogue pieces (executed by the 8 epilogue warps: threadIdx.x in [64, 320))
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__device__ __forceinline__ void epi_stage_bias(const GemmArgs& g, int tile, float* bias_s) {
+  if constexpr (EPI != EPI_TOPK) {
+    // stage this tile's bias slice in shared memory while the MMAs of the tile are still running
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < BN; i += kEpiThreads) {
+      const int n = tile * BN + i;
+      bias_s[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.f;
+    }
+    named_bar_sync(1, kEpiThreads);
+  }
+}
+
+// Top-k over one 32-column chunk held in registers. Branch-free in the common case: one max-reduce
+// and one compare against the current k-th best. Only when some element qualifies does the (compact,
+// single-site) extraction loop run: take the maximum, insert it, knock it out, repeat. Equal values
+// are extracted lowest column first and inserted after their equals, so ties resolve to the lower
+// class index exactly as a column-order scan would.
+template <int KC>
+__device__ __forceinline__ void topk_chunk(uint32_t (&v)[32], int n0, int n_valid, TopK<KC>& top) {
+  if (n_valid < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= n_valid) v[j] = 0xff800000u;   // -inf
+  }
+  float m = __uint_as_float(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  while (m > top.s[KC - 1]) {
+    int jj = 31;
+#pragma unroll
+    for (int j = 30; j >= 0; --j) jj = (__uint_as_float(v[j]) == m) ? j : jj;
+    top.insert(m, n0 + jj);
+    float m2 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = (j == jj) ? 0xff800000u : v[j];
+      m2 = fmaxf(m2, __uint_as_float(v[j]));
+    }
+    m = m2;
+  }
+}
+
+// Write one 32x32 chunk (this thread: 32 consecutive values of row `lane`) into a per-warp staging
+// buffer laid out for a TMA store: bf16 rows of 64 B under SWIZZLE_64B, fp32 rows of 128 B under
+// SWIZZLE_128B (16-byte unit index XORed with the row bits TMA expects) - conflict-free stores.
+template <int EPI>
+__device__ __forceinline__ void stage_chunk(uint8_t* stg, int lane, const float (&f)[32]) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+    uint8_t* rowp = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+      w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+      w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+      w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+      *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = w;
+    }
+  } else {
+    uint8_t* rowp = stg + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  }
+}
+
+// Drain one accumulator buffer. tbase = TMEM address of (this warp's lane quadrant, buffer column 0);
+// stg = this warp's two staging buffers; row0 = first output row of this warp's lane quadrant.
 template <int BN, int EPI, int KC>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+__device__ __forceinline__ void epi_process(const GemmArgs& g, const CUtensorMap* tmC, int tile, uint32_t tbase,
+                                            const float* bias_s, uint8_t* stg, int half, int lane, int row0,
+                                            uint32_t& store_count, TopK<KC>& top) {
+  constexpr int NC = BN / 32;   // 32-column chunks per tile
+  constexpr int NCW = NC / 2;   // chunks per warp (two warps per lane quadrant)
+  if constexpr (EPI == EPI_TOPK) {
+#pragma unroll 1
+    for (int cw = 0; cw < NCW; ++cw) {
+      const int c = 2 * cw + half;
+      const int n0 = tile * BN + c * 32;
+      if (n0 >= g.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_wait_dep(v);
+      topk_chunk<KC>(v, n0, g.N - n0, top);
+    }
+  } else {
+    constexpr int STG = epi_stage_bytes(EPI);
+    const int row = row0 + lane;
+    uint32_t v[2][32];
+    tmem_ld_32x32(tbase + static_cast<uint32_t>(half * 32), v[0]);
+#pragma unroll
+    for (int cw = 0; cw < NCW; ++cw) {
+      const int c = 2 * cw + half;
+      const int n0 = tile * BN + c * 32;
+      tmem_ld_wait_dep(v[cw & 1]);
+      if (cw + 1 < NCW) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 2) * 32), v[(cw + 1) & 1]);  // overlaps the math below
+      if (n0 >= g.N) continue;  // warp-uniform
+      const uint32_t (&vc)[32] = v[cw & 1];
+      float f[32];
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = b4[j];
+        f[4 * j + 0] = __uint_as_float(vc[4 * j + 0]) + b.x;
+        f[4 * j + 1] = __uint_as_float(vc[4 * j + 1]) + b.y;
+        f[4 * j + 2] = __uint_as_float(vc[4 * j + 2]) + b.z;
+        f[4 * j + 3] = __uint_as_float(vc[4 * j + 3]) + b.w;
+      }
+      if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+      }
+      if constexpr (EPI == EPI_BIAS_RES_F32) {
+        if (row < g.M) {
+          const float4* r4 = reinterpret_cast<const float4*>(g.residual + static_cast<size_t>(row) * g.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = __ldg(r4 + j);
+            f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+          }
+        }
+      }
+      // stage in swizzled shared memory, then one TMA store per 32x32 chunk (clipped at the edges)
+      uint8_t* buf = stg + (store_count & 1u) * STG;
+      if (lane == 0) bulk_wait_group_read<1>();   // the store that last used this buffer has read it
+      __syncwarp();
+      stage_chunk<EPI>(buf, lane, f);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, buf, n0, row0);
+        bulk_commit_group();
+      }
+      ++store_count;
+    }
+  }
+}
+
+template <int KC>
+__device__ __forceinline__ void epi_store_candidates(const GemmArgs& g, int half, int row, const TopK<KC>& top) {
+  if (row < g.M) {
+    // each (column split, chunk parity) pair contributes its own candidate list
+    const size_t base = (static_cast<size_t>(blockIdx.y * 2 + half) * g.M + row) * KC;
+#pragma unroll
+    for (int i = 0; i < KC; ++i) { g.cand_score[base + i] = top.s[i]; g.cand_idx[base + i] = top.id[i]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per 128 rows
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI, int KC>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer arithmetic on the __shared__ array itself so accesses stay in the shared window
   // (LDS/STS) instead of degrading to generic loads; SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stg_all = tiles + STAGES * Cfg::STAGE_BYTES;                    // [8 warps][2][STG_BYTES], 1024-aligned
+  uint8_t* tail = stg_all + kEpiWarps * 2 * Cfg::STG_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* bias_smem = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256);   // [2][BN]
+  float* bias_smem = reinterpret_cast<float*>(tail + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,8 +304,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI != EPI_TOPK) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], Cfg::EPI_THREADS / 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -167,116 +365,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else {
     // ---------------- epilogue (warps 2..9): two warps per TMEM lane quadrant ----------------
-    // Warp w may only touch TMEM lanes [32*(w&3), +32); the two warps of a quadrant take alternate
-    // 32-column chunks, so one warp's tcgen05.ld latency hides behind the other's math and stores.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;   // 0 | 1
-    const int row = m_blk * BM + q * 32 + lane;
-    const bool row_ok = row < g.M;
+    const int row0 = m_blk * BM + q * 32;
+    uint8_t* stg = stg_all + (warp - 2) * 2 * Cfg::STG_BYTES;
+    uint32_t store_count = 0;
     TopK<KC> top;
     if constexpr (EPI == EPI_TOPK) top.init();
-    const int et = threadIdx.x - 64;    // 0..255 within the epilogue group
-    constexpr int NC = BN / 32;         // chunks per tile
-    constexpr int NCW = NC / 2;         // chunks per warp
     int t = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++t) {
       const int buf = t & 1;
       const uint32_t use = static_cast<uint32_t>(t >> 1);
       float* bias_s = bias_smem + buf * BN;
-      if constexpr (EPI != EPI_TOPK) {
-        // stage this tile's bias slice in shared memory while the MMAs of the tile are still running
-        for (int i = et; i < BN; i += Cfg::EPI_THREADS) {
-          const int n = tile * BN + i;
-          bias_s[i] = (g.bias != nullptr && n < g.N) ? __ldg(g.bias + n) : 0.f;
-        }
-        named_bar_sync(1, Cfg::EPI_THREADS);
-      }
+      epi_stage_bias<BN, EPI>(g, tile, bias_s);
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      if constexpr (EPI == EPI_TOPK) {
-        // code kept small on purpose (32 inlined offers): the sweep runs hundreds of tiles
-#pragma unroll 1
-        for (int cw = 0; cw < NCW; ++cw) {
-          const int c = 2 * cw + half;
-          const int n0 = tile * BN + c * 32;
-          if (n0 >= g.N) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
-          tmem_ld_wait_dep(v);
-          if (n0 + 32 <= g.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) top.offer(__uint_as_float(v[j]), n0 + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) top.offer(__uint_as_float(v[j]), n0 + j);
-          }
-        }
-      } else {
-        uint32_t v[2][32];
-        tmem_ld_32x32(tbase + static_cast<uint32_t>(half * 32), v[0]);
-#pragma unroll
-        for (int cw = 0; cw < NCW; ++cw) {
-          const int c = 2 * cw + half;
-          const int n0 = tile * BN + c * 32;
-          tmem_ld_wait_dep(v[cw & 1]);
-          if (cw + 1 < NCW) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 2) * 32), v[(cw + 1) & 1]);  // overlaps the math below
-          if (n0 >= g.N || !row_ok) continue;
-          const uint32_t (&vc)[32] = v[cw & 1];
-          float f[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
-            f[4 * j + 0] = __uint_as_float(vc[4 * j + 0]) + b.x;
-            f[4 * j + 1] = __uint_as_float(vc[4 * j + 1]) + b.y;
-            f[4 * j + 2] = __uint_as_float(vc[4 * j + 2]) + b.z;
-            f[4 * j + 3] = __uint_as_float(vc[4 * j + 3]) + b.w;
-          }
-          const size_t off = static_cast<size_t>(row) * g.ldo + n0;
-          if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-            if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
-            }
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              o[j] = w;
-            }
-          } else {
-            if constexpr (EPI == EPI_BIAS_RES_F32) {
-              const float4* r4 = reinterpret_cast<const float4*>(g.residual + off);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = __ldg(r4 + j);
-                f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-              }
-            }
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-        }
-      }
+      epi_process<BN, EPI, KC>(g, &tmC, tile, tbase, bias_s, stg, half, lane, row0, store_count, top);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-    if constexpr (EPI == EPI_TOPK) {
-      if (row_ok) {
-        // each (column split, chunk parity) pair contributes its own candidate list
-        const size_t base = (static_cast<size_t>(blockIdx.y * 2 + half) * g.M + row) * KC;
-#pragma unroll
-        for (int i = 0; i < KC; ++i) { g.cand_score[base + i] = top.s[i]; g.cand_idx[base + i] = top.id[i]; }
-      }
-    }
+    if constexpr (EPI == EPI_TOPK) epi_store_candidates<KC>(g, half, row0 + lane, top);
+    else if (lane == 0) bulk_wait_group<0>();   // staged tiles fully written before the CTA retires
   }
 
   tc_fence_before();
@@ -285,6 +396,159 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA pair per 256 rows (cluster of 2, cta_group::2)
+// ------------------------------------------------------------------------------------------------
+// Protocol (rank 0 = leader, issues every MMA for the pair):
+//   full[s]   lives in the LEADER: expect_tx covers the bytes of BOTH CTAs' TMA loads of stage s;
+//             each CTA's loads complete_tx on the leader's barrier (cta_group::2 TMA)
+//   empty[s]  one per CTA: the leader's tcgen05.commit is multicast to both, freeing the stage in each
+//   tfull[b]  one per CTA (multicast commit): accumulator b complete in this CTA's TMEM
+//   tempty[b] lives in the LEADER: all 16 epilogue warps of the pair arrive (the peer's remotely)
+//   afull     (ARES) lives in the LEADER: both CTAs' resident A blocks have landed
+template <int BN, int EPI, int KC, bool ARES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+           const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  using Cfg = Gemm2Cfg<BN, EPI, ARES>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ares = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // resident A block (ARES)
+  uint8_t* tiles = ares + Cfg::ARES_BYTES;
+  uint8_t* stg_all = tiles + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* tail = stg_all + kEpiWarps * 2 * Cfg::STG_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+  float* bias_smem = reinterpret_cast<float*>(tail + 256);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_blk = blockIdx.x;                       // blocks 2p, 2p+1 form pair p: rows [128*m_blk, +128)
+  const int tiles_total = (g.N + BN - 1) / BN;
+  const int tile0 = blockIdx.y * g.tiles_per_cta;
+  const int tile1 = min(tile0 + g.tiles_per_cta, tiles_total);
+  const int num_kb = g.K / BK;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if constexpr (EPI != EPI_TOPK) tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * kEpiWarps); }
+    mbar_init(afull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (each CTA loads its own A rows and its half of W) ----------------
+      if constexpr (ARES) {
+        const uint32_t bar = mapa_u32(smem_u32(afull), 0);
+        if (leader) mbar_expect_tx(afull, 2u * static_cast<uint32_t>(num_kb) * Cfg::A_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d_2sm(ares + kb * Cfg::A_BYTES, &tmA, bar, kb * BK, m_blk * BM);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
+          const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+          if (leader) mbar_expect_tx(&full[stage], 2u * Cfg::STAGE_BYTES);
+          if constexpr (!ARES) {
+            tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m_blk * BM);
+            sa += Cfg::A_BYTES;
+          }
+          tma_load_2d_2sm(sa, &tmB, bar, kb * BK, tile * BN + static_cast<int>(rank) * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader only): UMMA 256 x BN x 16 across the pair ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      if constexpr (ARES) {
+        mbar_wait(afull, 0);
+        tc_fence_after();
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = tile0; tile < tile1; ++tile, ++t) {
+        const int buf = t & 1;
+        const uint32_t use = static_cast<uint32_t>(t >> 1);
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t s_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = ARES ? smem_u32(ares + kb * Cfg::A_BYTES) : s_addr;
+          const uint32_t b_addr = ARES ? s_addr : s_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16_2sm(d_tmem, make_sw128_kmajor_desc(a_addr + k * 32), make_sw128_kmajor_desc(b_addr + k * 32),
+                         idesc, static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit_2sm(&empty[stage]);  // multicast: frees the stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull[buf]);      // multicast: accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..9 of BOTH CTAs, each on its own 128 rows) ----------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row0 = m_blk * BM + q * 32;
+    uint8_t* stg = stg_all + (warp - 2) * 2 * Cfg::STG_BYTES;
+    uint32_t store_count = 0;
+    TopK<KC> top;
+    if constexpr (EPI == EPI_TOPK) top.init();
+    int t = 0;
+    for (int tile = tile0; tile < tile1; ++tile, ++t) {
+      const int buf = t & 1;
+      const uint32_t use = static_cast<uint32_t>(t >> 1);
+      float* bias_s = bias_smem + buf * BN;
+      epi_stage_bias<BN, EPI>(g, tile, bias_s);
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      epi_process<BN, EPI, KC>(g, &tmC, tile, tbase, bias_s, stg, half, lane, row0, store_count, top);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
+    }
+    if constexpr (EPI == EPI_TOPK) epi_store_candidates<KC>(g, half, row0 + lane, top);
+    else if (lane == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's shared memory and TMEM must outlive the leader's last MMA
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -28,11 +28,14 @@ def _bf16_round(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("tile_n", [128, 192, 256])
+# tile_n: column-tile width; +1000 = CTA-pair kernel (cta_group::2); +2000 = CTA pair with resident A block
+@pytest.mark.parametrize("tile_n", [128, 192, 256, 1128, 1192, 1256, 2128, 2192, 2256])
 @pytest.mark.parametrize("shape", [(128, 192, 64), (300, 384, 384), (1000, 1152, 384), (257, 1536, 384),
                                    (4096, 384, 1536), (129, 32, 128), (20000, 768, 768)])
 def test_tcgen05_gemm_matches_torch(tiny_engine, shape, tile_n):
     m, n, k = shape
+    if tile_n >= 2000 and k > 384:
+        pytest.skip("resident-A variant holds at most K = 384")
     g = torch.Generator(device="cuda").manual_seed(m * 7 + n * 3 + k)
     a = torch.randn(m, k, device="cuda", generator=g)
     w = torch.randn(n, k, device="cuda", generator=g) * 0.05
