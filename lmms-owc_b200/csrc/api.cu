@@ -550,20 +550,25 @@ static int launch_attn(owc_encoder* e, const AttnArgs& aa) {
   return check_launch(c, "k_attn");
 }
 
-// bf16 production path for sequences of at most 64 tokens: tensor-core attention, CTA per sequence.
+// bf16 production path for sequences of at most 64 tokens: tensor-core attention, one persistent warp
+// per (sequence, head) pair.
 static int launch_attn_mma(owc_encoder* e, const AttnArgs& aa) {
   owc_ctx* c = e->ctx;
   const int D = e->arch.hidden / e->arch.heads;
+  const long long pairs = static_cast<long long>(aa.n_seq) * aa.heads;
   ProfScope prof(c, OWC_KCAT_ATTN);
 #define ATTN_MMA_LAUNCH(DD, TP)                                                                             \
   do {                                                                                                      \
-    using Cfg = AttnMmaCfg<DD, TP>;                                                                         \
+    constexpr int smem = AttnWarpCfg<DD>::smem_bytes(TP);                                                   \
     static bool attr_done = false;                                                                          \
-    if (Cfg::SMEM_BYTES > 48 * 1024 && !attr_done) {                                                        \
-      CU_OK(cudaFuncSetAttribute(k_attn_mma<DD, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); \
+    if (smem > 48 * 1024 && !attr_done) {                                                                   \
+      CU_OK(cudaFuncSetAttribute(k_attn_mma<DD, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
       attr_done = true;                                                                                     \
     }                                                                                                       \
-    k_attn_mma<DD, TP><<<aa.n_seq, 128, Cfg::SMEM_BYTES, c->stream>>>(aa);                                  \
+    const int per_sm = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));                             \
+    const long long want = (pairs + 3) / 4;                                                                 \
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(c->sm_count) * per_sm)); \
+    k_attn_mma<DD, TP><<<grid, 128, smem, c->stream>>>(aa);                                                 \
   } while (0)
   if (D == 32) {
     if (aa.max_t <= 16) ATTN_MMA_LAUNCH(32, 16);

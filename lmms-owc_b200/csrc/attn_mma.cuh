@@ -1,15 +1,18 @@
 // attn_mma.cuh - short-sequence (<= 64 token) self-attention for the production (bf16) mode.
 //
-// One CTA per sequence, one warp per head, heads processed four at a time. The sequence's Q/K/V
-// slices are staged in shared memory with coalesced 16-byte loads (Q, K row-major [t][d]; V transposed
-// [d][t]; row pitches chosen so every fragment load is bank-conflict free), the two small products
-// QK^T and PV run on the warp-level tensor-core path (mma.sync m16n8k16 bf16 -> fp32: a sequence is
-// 3..64 tokens, far below the 128-row tcgen05 tile), the softmax lives in registers with quad
-// shuffles, probabilities are rounded to bf16 only as the PV operand, and the output is staged back
-// through shared memory for coalesced 16-byte stores. Packed sequences have no padding, so the
-// reference's additive padding mask (modeling_bert.py:114-140) is a no-op and only the tile padding
-// (keys >= T) is masked. MPNet's relative-position bias (modeling_mpnet.py:163-173, 324-362) comes
-// from the per-head LUT indexed by (key - query).
+// One WARP per (sequence, head), no block-level synchronisation: each warp stages its head's Q/K/V
+// slices (T x D bf16 each, 64-128 B rows) into a private shared-memory region with 16-byte loads,
+// runs the two small products QK^T and PV on the warp-level tensor-core path (mma.sync m16n8k16
+// bf16 -> fp32; a sequence is 3..64 tokens, far below the 128-row tcgen05 tile), keeps the softmax in
+// registers (quad shuffles), rounds probabilities to bf16 only as the PV operand, and stages the
+// output back through its region for 16-byte coalesced stores. Warps are persistent (grid-stride over
+// the pairs) and pick the smallest tile padding (16/32/64) per sequence, so a 7-token label costs one
+// m-tile and one key block regardless of the longest sequence in the chunk.
+//   Row pitch D+8 elements: every fragment load (Q/K as 32-bit pairs, V via ldmatrix.trans) and every
+//   16-byte staging store is bank-conflict free.
+// Packed sequences have no padding, so the reference's additive padding mask (modeling_bert.py:114-140)
+// is a no-op and only the tile padding (keys >= T) is masked. MPNet's relative-position bias
+// (modeling_mpnet.py:163-173, 324-362) comes from the per-head LUT indexed by (key - query).
 #pragma once
 
 #include "common.cuh"
@@ -24,166 +27,179 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// Two transposed 8x8 b16 matrices: the B fragment (k = key, n = dim) of a row-major [key][dim] tile.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&b)[2], const void* row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+               : "=r"(b[0]), "=r"(b[1])
+               : "r"(smem_u32(row_ptr)));
+}
 
-template <int D, int TP>
-struct AttnMmaCfg {
-  static constexpr int QK_PITCH = D + 8;    // bf16 elements; (D+8)*2 B rows: conflict-free fragment loads
-  static constexpr int VT_PITCH = TP + 8;
-  static constexpr int HEAD_ELEMS = 2 * TP * QK_PITCH + D * VT_PITCH;
-  static constexpr int SMEM_BYTES = 4 * HEAD_ELEMS * 2;   // four heads in flight
+template <int D>
+struct AttnWarpCfg {
+  static constexpr int PITCH = D + 8;                       // bf16 elements per staged row
+  __host__ __device__ static constexpr int region_elems(int tpmax) { return 3 * tpmax * PITCH; }
+  __host__ __device__ static constexpr int smem_bytes(int tpmax) { return 4 * region_elems(tpmax) * 2; }   // 4 warps per CTA
 };
 
+// One (sequence, head) pair with tile padding TP, entirely inside the calling warp.
 template <int D, int TP>
-__global__ void __launch_bounds__(128) k_attn_mma(const AttnArgs a) {
-  using Cfg = AttnMmaCfg<D, TP>;
-  constexpr int QP = Cfg::QK_PITCH, VP = Cfg::VT_PITCH;
+__device__ __forceinline__ void attn_pair(const AttnArgs& a, __nv_bfloat16* reg, int tpmax, int lane, int beg, int T,
+                                          int head, float scale_log2) {
+  constexpr int P = AttnWarpCfg<D>::PITCH;
   constexpr int NT = TP / 8;     // key n-tiles of S
   constexpr int MT = TP / 16;    // query m-tiles
   constexpr int DN = D / 8;      // output n-tiles
-  constexpr int CPR = D / 8;     // 16-byte chunks per (token, part, head)
-  extern __shared__ __align__(16) uint8_t smem_attn[];
-  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CPR = D / 8;     // 16-byte chunks per staged row
   const int g = lane >> 2, t4 = lane & 3;
-  const int seq = blockIdx.x;
-  const int beg = a.cu[a.seq0 + seq] - a.tok0;
-  const int T = a.cu[a.seq0 + seq + 1] - a.tok0 - beg;
-  if (T <= 0) return;
   const int H = a.H;
-  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a.qkv) + static_cast<size_t>(beg) * 3 * H;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(beg) * H;
+  __nv_bfloat16* Qh = reg;
+  __nv_bfloat16* Kh = reg + tpmax * P;
+  __nv_bfloat16* Vh = reg + 2 * tpmax * P;
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a.qkv) + static_cast<size_t>(beg) * 3 * H + head * D;
 
-  // zero once: padded V columns must be finite zeros (0 * garbage could be NaN); loads never touch padding
-  for (int i = threadIdx.x; i < Cfg::SMEM_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem_attn)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
+  // ---- stage Q, K, V rows of this head (row-major) ----
+  for (int idx = lane; idx < T * 3 * CPR; idx += 32) {
+    const int c = idx % CPR;
+    const int p = (idx / CPR) % 3;
+    const int t = idx / (3 * CPR);
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(t) * 3 * H + p * H + c * 8);
+    *reinterpret_cast<uint4*>(reg + (p * tpmax + t) * P + c * 8) = v;
+  }
+  __syncwarp();
 
-  const float scale_log2 = a.scale * 1.4426950408889634f;
-  for (int h0 = 0; h0 < a.heads; h0 += 4) {
-    const int nh = min(4, a.heads - h0);
-    // ---- stage Q, K (row-major) and V (transposed) of heads h0..h0+nh-1 ----
-    const int chunks = T * 3 * nh * CPR;
-    for (int idx = threadIdx.x; idx < chunks; idx += 128) {
-      const int c = idx % CPR;
-      const int hh = (idx / CPR) % nh;
-      const int p = (idx / (CPR * nh)) % 3;
-      const int t = idx / (CPR * nh * 3);
-      const uint4 v = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(t) * 3 * H + p * H + (h0 + hh) * D + c * 8);
-      __nv_bfloat16* hb = sm + hh * Cfg::HEAD_ELEMS;
-      if (p < 2) {
-        *reinterpret_cast<uint4*>(hb + p * TP * QP + t * QP + c * 8) = v;
-      } else {
-        __nv_bfloat16* vt = hb + 2 * TP * QP;
-        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+  const float* lut = a.rel_lut ? a.rel_lut + static_cast<size_t>(head) * (2 * a.max_pos - 1) + a.max_pos - 1 : nullptr;
+#pragma unroll 1
+  for (int mt = 0; mt < MT; ++mt) {
+    if (mt * 16 >= T) break;
+    float s[NT][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vt[(c * 8 + i) * VP + t] = e[i];
+    for (int nt = 0; nt < NT; ++nt) { s[nt][0] = 0.f; s[nt][1] = 0.f; s[nt][2] = 0.f; s[nt][3] = 0.f; }
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      uint32_t af[4];
+      af[0] = *reinterpret_cast<const uint32_t*>(Qh + r0 * P + ks * 16 + t4 * 2);
+      af[1] = *reinterpret_cast<const uint32_t*>(Qh + r1 * P + ks * 16 + t4 * 2);
+      af[2] = *reinterpret_cast<const uint32_t*>(Qh + r0 * P + ks * 16 + 8 + t4 * 2);
+      af[3] = *reinterpret_cast<const uint32_t*>(Qh + r1 * P + ks * 16 + 8 + t4 * 2);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt * 8 < T) {   // warp-uniform
+          uint32_t bf[2];
+          bf[0] = *reinterpret_cast<const uint32_t*>(Kh + (nt * 8 + g) * P + ks * 16 + t4 * 2);
+          bf[1] = *reinterpret_cast<const uint32_t*>(Kh + (nt * 8 + g) * P + ks * 16 + 8 + t4 * 2);
+          mma_bf16_16816(s[nt], af, bf);
+        }
       }
     }
-    __syncthreads();
-
-    if (warp < nh) {
-      const int head = h0 + warp;
-      __nv_bfloat16* Qh = sm + warp * Cfg::HEAD_ELEMS;
-      const __nv_bfloat16* Kh = Qh + TP * QP;
-      const __nv_bfloat16* Vt = Qh + 2 * TP * QP;
-      const float* lut = a.rel_lut ? a.rel_lut + static_cast<size_t>(head) * (2 * a.max_pos - 1) + a.max_pos - 1 : nullptr;
-#pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        if (mt * 16 >= T) break;
-        float s[NT][4];
+    // scale (log2 domain), relative bias, mask padded keys; row maxima
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { s[nt][0] = 0.f; s[nt][1] = 0.f; s[nt][2] = 0.f; s[nt][3] = 0.f; }
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 < T) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          uint32_t af[4];
-          af[0] = *reinterpret_cast<const uint32_t*>(Qh + r0 * QP + ks * 16 + t4 * 2);
-          af[1] = *reinterpret_cast<const uint32_t*>(Qh + r1 * QP + ks * 16 + t4 * 2);
-          af[2] = *reinterpret_cast<const uint32_t*>(Qh + r0 * QP + ks * 16 + 8 + t4 * 2);
-          af[3] = *reinterpret_cast<const uint32_t*>(Qh + r1 * QP + ks * 16 + 8 + t4 * 2);
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            if (nt * 8 < T) {   // warp-uniform
-              uint32_t bf[2];
-              bf[0] = *reinterpret_cast<const uint32_t*>(Kh + (nt * 8 + g) * QP + ks * 16 + t4 * 2);
-              bf[1] = *reinterpret_cast<const uint32_t*>(Kh + (nt * 8 + g) * QP + ks * 16 + 8 + t4 * 2);
-              mma_bf16_16816(s[nt], af, bf);
-            }
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int j = nt * 8 + t4 * 2 + (e & 1);
+          const int i = (e < 2) ? r0 : r1;
+          float v = s[nt][e] * scale_log2;
+          if (lut != nullptr && j < T && i < T) v += __ldg(lut + (j - i)) * 1.4426950408889634f;
+          v = (j < T) ? v : -INFINITY;
+          s[nt][e] = v;
+          if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
         }
-        // scale (in log2 domain), relative bias, mask padded keys; row maxima
-        float m0 = -INFINITY, m1 = -INFINITY;
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    // probabilities rounded to bf16 (the PV operand); row sums of the ROUNDED values
+    uint32_t pk[NT][2];
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 < T) {
+        float e0, e1, e2, e3;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s[nt][0] - m0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s[nt][1] - m0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(s[nt][2] - m1));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(s[nt][3] - m1));
+        const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+        const __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+        sum0 += __low2float(p01) + __high2float(p01);
+        sum1 += __low2float(p23) + __high2float(p23);
+        pk[nt][0] = *reinterpret_cast<const uint32_t*>(&p01);
+        pk[nt][1] = *reinterpret_cast<const uint32_t*>(&p23);
+      } else {
+        pk[nt][0] = 0u;
+        pk[nt][1] = 0u;
+      }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V  (V row-major; ldmatrix.trans yields the k=key, n=dim fragment)
+    float o[DN][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = nt * 8 + t4 * 2 + (e & 1);
-            const int i = (e < 2) ? r0 : r1;
-            float v = s[nt][e] * scale_log2;
-            if (lut != nullptr && j < T && i < T) v += __ldg(lut + (j - i)) * 1.4426950408889634f;
-            v = (j < T) ? v : -INFINITY;
-            s[nt][e] = v;
-            if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
-          }
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        // probabilities rounded to bf16 (the PV operand); row sums of the ROUNDED values
-        uint32_t pk[NT][2];
-        float sum0 = 0.f, sum1 = 0.f;
+    for (int dn = 0; dn < DN; ++dn) { o[dn][0] = 0.f; o[dn][1] = 0.f; o[dn][2] = 0.f; o[dn][3] = 0.f; }
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const __nv_bfloat162 p01 = __floats2bfloat162_rn(exp2f(s[nt][0] - m0), exp2f(s[nt][1] - m0));
-          const __nv_bfloat162 p23 = __floats2bfloat162_rn(exp2f(s[nt][2] - m1), exp2f(s[nt][3] - m1));
-          sum0 += __low2float(p01) + __high2float(p01);
-          sum1 += __low2float(p23) + __high2float(p23);
-          pk[nt][0] = *reinterpret_cast<const uint32_t*>(&p01);
-          pk[nt][1] = *reinterpret_cast<const uint32_t*>(&p23);
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        // O = P V
-        float o[DN][4];
-#pragma unroll
-        for (int dn = 0; dn < DN; ++dn) { o[dn][0] = 0.f; o[dn][1] = 0.f; o[dn][2] = 0.f; o[dn][3] = 0.f; }
-#pragma unroll
-        for (int kt = 0; kt < MT; ++kt) {
-          if (kt * 16 < T) {   // warp-uniform
-            uint32_t af[4] = {pk[2 * kt][0], pk[2 * kt][1], pk[2 * kt + 1][0], pk[2 * kt + 1][1]};
-#pragma unroll
-            for (int dn = 0; dn < DN; ++dn) {
-              uint32_t bf[2];
-              bf[0] = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + t4 * 2);
-              bf[1] = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + 8 + t4 * 2);
-              mma_bf16_16816(o[dn], af, bf);
-            }
-          }
-        }
-        // normalise; stage this head's output over its own (now dead) Q rows of this m-tile
-        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-        __syncwarp();
+    for (int kt = 0; kt < MT; ++kt) {
+      if (kt * 16 < T) {   // warp-uniform
+        const uint32_t af[4] = {pk[2 * kt][0], pk[2 * kt][1], pk[2 * kt + 1][0], pk[2 * kt + 1][1]};
+        const __nv_bfloat16* vrow = Vh + (kt * 16 + (lane & 15)) * P;
 #pragma unroll
         for (int dn = 0; dn < DN; ++dn) {
-          if (r0 < T) *reinterpret_cast<uint32_t*>(Qh + r0 * QP + dn * 8 + t4 * 2) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-          if (r1 < T) *reinterpret_cast<uint32_t*>(Qh + r1 * QP + dn * 8 + t4 * 2) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+          uint32_t bf[2];
+          ldmatrix_x2_trans(bf, vrow + dn * 8);
+          mma_bf16_16816(o[dn], af, bf);
         }
       }
     }
-    __syncthreads();
-    // ---- coalesced write-back of the staged outputs of these heads ----
-    const int ochunks = T * nh * CPR;
-    for (int idx = threadIdx.x; idx < ochunks; idx += 128) {
-      const int c = idx % CPR;
-      const int hh = (idx / CPR) % nh;
-      const int t = idx / (CPR * nh);
-      const uint4 v = *reinterpret_cast<const uint4*>(sm + hh * Cfg::HEAD_ELEMS + t * QP + c * 8);
-      *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * H + (h0 + hh) * D + c * 8) = v;
+    // normalise; stage this m-tile's output over its own (now dead) Q rows
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    __syncwarp();
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(Qh + r0 * P + dn * 8 + t4 * 2) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(Qh + r1 * P + dn * 8 + t4 * 2) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
     }
-    __syncthreads();
+  }
+  __syncwarp();
+  // ---- coalesced write-back (16 B per lane) ----
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(beg) * H + head * D;
+  for (int idx = lane; idx < T * CPR; idx += 32) {
+    const int c = idx % CPR;
+    const int t = idx / CPR;
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * H + c * 8) = *reinterpret_cast<const uint4*>(Qh + t * P + c * 8);
+  }
+  __syncwarp();   // region is reused by the next pair
+}
+
+template <int D, int TPMAX>
+__global__ void __launch_bounds__(128) k_attn_mma(const AttnArgs a) {
+  using Cfg = AttnWarpCfg<D>;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __nv_bfloat16* reg = reinterpret_cast<__nv_bfloat16*>(smem_attn) + warp * Cfg::region_elems(TPMAX);
+
+  // zero once: padded V rows must hold finite values (0 * garbage could be NaN); staging only ever
+  // writes finite activations afterwards
+  for (int i = lane; i < Cfg::region_elems(TPMAX) / 8; i += 32) reinterpret_cast<uint4*>(reg)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+
+  const float scale_log2 = a.scale * 1.4426950408889634f;
+  const long long pairs = static_cast<long long>(a.n_seq) * a.heads;
+  const long long stride = static_cast<long long>(gridDim.x) * 4;
+  for (long long p = static_cast<long long>(blockIdx.x) * 4 + warp; p < pairs; p += stride) {
+    const int seq = static_cast<int>(p / a.heads);
+    const int head = static_cast<int>(p % a.heads);
+    const int beg = a.cu[a.seq0 + seq] - a.tok0;
+    const int T = a.cu[a.seq0 + seq + 1] - a.tok0 - beg;
+    if (T <= 0) continue;
+    if (TPMAX == 16 || T <= 16) attn_pair<D, 16>(a, reg, TPMAX, lane, beg, T, head, scale_log2);
+    else if (TPMAX == 32 || T <= 32) attn_pair<D, (TPMAX >= 32 ? 32 : 16)>(a, reg, TPMAX, lane, beg, T, head, scale_log2);
+    else attn_pair<D, (TPMAX >= 64 ? 64 : 16)>(a, reg, TPMAX, lane, beg, T, head, scale_log2);
   }
 }
 
