@@ -62,7 +62,12 @@ struct owc_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int chunk_tokens = 0;
-  int gemm_mode = 2;   // 0: 1-CTA tcgen05, 1: CTA pairs, 2: CTA pairs + resident A (env OWC_GEMM_MODE)
+  // tcgen05 kernel variant: 0 = one CTA per 128 rows, 1 = CTA pairs (cta_group::2), 2 = CTA pairs + resident A.
+  // Measured on B200: the encoder's short sweeps (2-8 column tiles per row block) run fastest on the 1-CTA
+  // kernel, the similarity sweep (hundreds of tiles) on pairs with the A block resident.
+  int gemm_mode = 0;       // encoder contractions (env OWC_GEMM_MODE)
+  int sim_mode = 2;        // similarity + top-k     (env OWC_SIM_MODE)
+  int fuse_ln = 1;         // fuse residual+LayerNorm into the O-proj / FFN2 epilogue (env OWC_FUSE_LN)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -96,6 +101,7 @@ struct owc_encoder {
   float *qkv32 = nullptr, *ao32 = nullptr, *f32 = nullptr;   // check mode, allocated on first use
   CUtensorMap tm_xb, tm_ao, tm_f;            // A-operand maps (box 128 rows x 64)
   CUtensorMap tmo_qkv, tmo_f, tmo_y;         // epilogue TMA-store maps (box 32 x 32)
+  CUtensorMap tmo_x, tmo_xb;                 // fused-LN epilogue: residual stream (fp32, load + store) and its bf16 copy
 };
 
 constexpr int kEncBN = 192;   // divides 3H, H and I of both architectures (1152/384/1536, 2304/768/3072)
@@ -207,7 +213,7 @@ static int check_gemm_shape(const GemmArgs& g, int epi) {
 
 template <int BN, int EPI, int KC>
 static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
-                          int splits) {
+                          int splits, const CUtensorMap* td = nullptr) {
   using Cfg = GemmCfg<BN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -221,7 +227,9 @@ static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& 
   const int gy = (tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
   dim3 grid((g.M + 127) / 128, gy);
   ProfScope prof(c, EPI == EPI_TOPK ? OWC_KCAT_SIM : OWC_KCAT_GEMM);
-  k_gemm_tc<BN, EPI, KC><<<grid, kGemmThreads, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, tc, g);
+  if (EPI == EPI_RES_LN && (g.N != 2 * BN || gy != 1 || !td || !g.gamma || !g.beta))
+    return fail("fused LayerNorm epilogue needs N == %d and whole rows per CTA", 2 * BN);
+  k_gemm_tc<BN, EPI, KC><<<grid, kGemmThreads, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, tc, td ? *td : tc, g);
   return check_launch(c, "k_gemm_tc");
 }
 
@@ -317,6 +325,8 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char* gm = getenv("OWC_GEMM_MODE")) c->gemm_mode = std::max(0, std::min(2, atoi(gm)));
+  if (const char* sm = getenv("OWC_SIM_MODE")) c->sim_mode = std::max(0, std::min(2, atoi(sm)));
+  if (const char* fl = getenv("OWC_FUSE_LN")) c->fuse_ln = atoi(fl) != 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -507,7 +517,8 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   if (make_tmap(c, &e->tm_xb, e->xb, cap, h, 128) || make_tmap(c, &e->tm_ao, e->ao, cap, h, 128) ||
       make_tmap(c, &e->tm_f, e->f, cap, I, 128)) { owc_encoder_destroy(e); return 1; }
   if (make_out_tmap(c, &e->tmo_qkv, e->qkv, cap, 3 * h, true) || make_out_tmap(c, &e->tmo_f, e->f, cap, I, true) ||
-      make_out_tmap(c, &e->tmo_y, e->y, cap, h, false)) { owc_encoder_destroy(e); return 1; }
+      make_out_tmap(c, &e->tmo_y, e->y, cap, h, false) || make_out_tmap(c, &e->tmo_x, e->x, cap, h, false) ||
+      make_out_tmap(c, &e->tmo_xb, e->xb, cap, h, true)) { owc_encoder_destroy(e); return 1; }
   LOAD_CU(cudaStreamSynchronize(c->stream));  // `weights` may be freed by the caller after return
 #undef LOAD_CU
 #undef LOAD_FAIL
@@ -619,8 +630,13 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
   aa.rel_lut = e->rel_lut; aa.max_pos = a.max_pos;
 
   const int ln_grid = (M + 7) / 8;
+  // The residual+LayerNorm tail is fused into the O-projection / FFN2 epilogue when a whole row fits
+  // the two TMEM accumulator buffers (H == 2 * kEncBN, i.e. the MiniLM width) and the 1-CTA kernel runs.
+  const bool fuse_ln = bf && H == 2 * kEncBN && c->gemm_mode == 0 && c->fuse_ln;
   for (int l = 0; l < a.layers; ++l) {
     const LayerW& L = e->layers[l];
+    const bool last = l + 1 == a.layers;
+    // ---- attention block ----
     if (bf) {
       GemmArgs g{};
       g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
@@ -629,36 +645,52 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
       if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
       else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
       g = GemmArgs{};
-      g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = e->x; g.ldo = H;
-      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, L.tm2_wo, e->tmo_y, g)));
+      g.M = M; g.N = H; g.K = H; g.bias = L.bo;
+      if (fuse_ln) {
+        g.gamma = L.ln1g; g.beta = L.ln1b; g.ln_eps = a.ln_eps;
+        OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_ao, L.tm_wo, e->tmo_x, g, 1, &e->tmo_xb)));
+      } else {
+        g.residual = e->x; g.ldo = H;
+        OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, L.tm2_wo, e->tmo_y, g)));
+      }
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS>(c, e->x, L.wqkv32, L.bqkv, nullptr, e->qkv32, M, 3 * H, H, 3 * H));
       aa.qkv = e->qkv32; aa.out = e->ao32;
       OWC_TRY(launch_attn<float>(e, aa));
       OWC_TRY(launch_gemm_f32<EPF_BIAS_RES>(c, e->ao32, L.wo32, L.bo, e->x, e->y, M, H, H, H));
     }
-    {
-      ProfScope prof(c, OWC_KCAT_LN);
-      DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln1g, L.ln1b, a.ln_eps, e->x, bf ? e->xb : nullptr));
+    if (!fuse_ln) {
+      {
+        ProfScope prof(c, OWC_KCAT_LN);
+        DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln1g, L.ln1b, a.ln_eps, e->x, bf ? e->xb : nullptr));
+      }
+      OWC_TRY(check_launch(c, "k_ln"));
     }
-    OWC_TRY(check_launch(c, "k_ln"));
+    // ---- feed-forward block ----
     if (bf) {
       GemmArgs g{};
       g.M = M; g.N = I; g.K = H; g.bias = L.b1;
       OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, e->tm_xb, L.tm_w1, L.tm2_w1, e->tmo_f, g)));
       g = GemmArgs{};
-      g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = e->x; g.ldo = H;
-      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, L.tm2_w2, e->tmo_y, g)));
+      g.M = M; g.N = H; g.K = I; g.bias = L.b2;
+      if (fuse_ln) {
+        g.gamma = L.ln2g; g.beta = L.ln2b; g.ln_eps = a.ln_eps;
+        OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_f, L.tm_w2, e->tmo_x, g, 1, &e->tmo_xb)));
+      } else {
+        g.residual = e->x; g.ldo = H;
+        OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, L.tm2_w2, e->tmo_y, g)));
+      }
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS_GELU>(c, e->x, L.w132, L.b1, nullptr, e->f32, M, I, H, I));
       OWC_TRY(launch_gemm_f32<EPF_BIAS_RES>(c, e->f32, L.w232, L.b2, e->x, e->y, M, H, I, H));
     }
-    const bool last = l + 1 == a.layers;
-    {
-      ProfScope prof(c, OWC_KCAT_LN);
-      DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln2g, L.ln2b, a.ln_eps, e->x, (bf && !last) ? e->xb : nullptr));
+    if (!fuse_ln) {
+      {
+        ProfScope prof(c, OWC_KCAT_LN);
+        DISPATCH_NV(H, k_ln<NV><<<ln_grid, 256, 0, c->stream>>>(e->y, M, H, L.ln2g, L.ln2b, a.ln_eps, e->x, (bf && !last) ? e->xb : nullptr));
+      }
+      OWC_TRY(check_launch(c, "k_ln"));
     }
-    OWC_TRY(check_launch(c, "k_ln"));
   }
   {
     ProfScope prof(c, OWC_KCAT_POOL);
@@ -764,8 +796,8 @@ extern "C" int32_t owc_pair_dot(owc_ctx* c, const float* a, int64_t na, const in
 template <int BN, int KC>
 static int sim_candidates(owc_ctx* c, const __nv_bfloat16* zpb, long long n, const __nv_bfloat16* zcb, int C, int dim,
                           int* splits_out) {
-  const bool pair = c->gemm_mode != 0;
-  const bool ares = c->gemm_mode == 2 && dim <= kAresMaxK;
+  const bool pair = c->sim_mode != 0;
+  const bool ares = c->sim_mode == 2 && dim <= kAresMaxK;
   CUtensorMap ta, tb;
   OWC_TRY(make_tmap(c, &ta, zpb, static_cast<uint64_t>(n), dim, 128));
   OWC_TRY(make_tmap(c, &tb, zcb, static_cast<uint64_t>(C), dim, pair ? BN / 2 : BN));

@@ -34,7 +34,8 @@ enum : int {
   EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
   EPI_BIAS_RES_F32 = 2,    // out fp32 = acc + bias + residual   (pre-LayerNorm sum)
   EPI_BIAS_F32 = 3,        // out fp32 = acc (+ bias)            (debug / check of the mainloop)
-  EPI_TOPK = 4             // per-row top-KC candidates over all columns handled by this CTA
+  EPI_TOPK = 4,            // per-row top-KC candidates over all columns handled by this CTA
+  EPI_RES_LN = 5           // x = LayerNorm(acc + bias + x) in place (fp32) + bf16 copy; N == 2*BN (whole rows in TMEM)
 };
 
 struct GemmArgs {
@@ -45,6 +46,9 @@ struct GemmArgs {
   int ldo;                 // leading dimension of `residual`
   float* cand_score;       // EPI_TOPK: [2 * gridDim.y, M, KC] (two chunk parities per column split)
   int* cand_idx;
+  const float* gamma;      // EPI_RES_LN: LayerNorm weight / bias [N] and epsilon
+  const float* beta;
+  float ln_eps;
 };
 
 constexpr int kEpiWarps = 8;
@@ -57,7 +61,9 @@ __host__ __device__ constexpr int epi_stage_bytes(int epi) {
   return epi == EPI_TOPK ? 0 : ((epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) ? 32 * 64 : 32 * 128);
 }
 __host__ __device__ constexpr int epi_fixed_bytes(int bn, int epi) {
-  return 1024 /*align slack*/ + 256 /*barriers*/ + 2 * bn * 4 /*bias*/ + kEpiWarps * 2 * epi_stage_bytes(epi);
+  // EPI_RES_LN: 4 epilogue warps x 2 residual/staging buffers of 4 KB, and bias|gamma|beta of a whole row (2*bn each)
+  return epi == EPI_RES_LN ? 1024 + 512 + 3 * 2 * bn * 4 + 4 * 2 * 4096
+                           : 1024 /*align slack*/ + 512 /*barriers*/ + 2 * bn * 4 /*bias*/ + kEpiWarps * 2 * epi_stage_bytes(epi);
 }
 __host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
 
@@ -71,6 +77,7 @@ struct GemmCfg {
   static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI)) / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int STG_BYTES = epi_stage_bytes(EPI);
+  static constexpr int STG_TOTAL = (EPI == EPI_RES_LN) ? 4 * 2 * 4096 : kEpiWarps * 2 * STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
@@ -260,6 +267,100 @@ __device__ __forceinline__ void epi_process(const GemmArgs& g, const CUtensorMap
   }
 }
 
+// Fused residual + LayerNorm epilogue (EPI_RES_LN): N == 2*BN, so a row-block's whole rows sit in the
+// two TMEM accumulator buffers and thread r owns row r end to end - the statistics need no cross-
+// thread traffic at all. Executed by ONE warp per TMEM lane quadrant (warps 2..5).
+//   pass 1  v = acc + bias + residual: residual tiles (32x32 fp32) stream in by TMA, double-buffered
+//           in this warp's two 4 KB buffers; v is written back to TMEM (tcgen05.st); row sum
+//   pass 2  re-read TMEM: sum of (v - mean)^2  (two-pass variance, like nn.LayerNorm)
+//   pass 3  re-read TMEM: y = (v - mean) * rstd * gamma + beta -> fp32 tile staged in the same two
+//           buffers and TMA-stored over the residual (x is updated in place), bf16 tile staged in the
+//           (by now idle) pipeline ring and TMA-stored to the operand copy
+template <int BN>
+__device__ __forceinline__ void epi_res_ln(const GemmArgs& g, const CUtensorMap* tmX, const CUtensorMap* tmXb,
+                                           uint32_t tmem_q, uint64_t* tfull, uint64_t* rbar, uint8_t* buf2,
+                                           uint8_t* ring_bf16, const float* bias_s, const float* gamma_s,
+                                           const float* beta_s, int lane, int row0) {
+  constexpr int NC = 2 * BN / 32;   // 32-column chunks of a whole row
+  const int sw = lane & 7;
+  const float inv_n = 1.0f / static_cast<float>(2 * BN);
+  if (lane == 0) {
+    mbar_expect_tx(&rbar[0], 4096);
+    tma_load_2d(buf2, tmX, &rbar[0], 0, row0);
+  }
+  float sum = 0.f;
+  uint32_t v[32];
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    if (k == 0) { mbar_wait(&tfull[0], 0); tc_fence_after(); }
+    if (k == NC / 2) { mbar_wait(&tfull[1], 0); tc_fence_after(); }
+    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
+    if (lane == 0 && k + 1 < NC) {   // prefetch the next residual tile into the other buffer
+      mbar_expect_tx(&rbar[(k + 1) & 1], 4096);
+      tma_load_2d(buf2 + ((k + 1) & 1) * 4096, tmX, &rbar[(k + 1) & 1], (k + 1) * 32, row0);
+    }
+    mbar_wait(&rbar[k & 1], static_cast<uint32_t>((k >> 1) & 1));
+    const uint8_t* rrow = buf2 + (k & 1) * 4096 + lane * 128;
+    tmem_ld_wait_dep(v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r = *reinterpret_cast<const float4*>(rrow + ((j ^ sw) << 4));
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + k * 32 + 4 * j);
+      const float x0 = __uint_as_float(v[4 * j + 0]) + b.x + r.x;
+      const float x1 = __uint_as_float(v[4 * j + 1]) + b.y + r.y;
+      const float x2 = __uint_as_float(v[4 * j + 2]) + b.z + r.z;
+      const float x3 = __uint_as_float(v[4 * j + 3]) + b.w + r.w;
+      sum += (x0 + x1) + (x2 + x3);
+      v[4 * j + 0] = __float_as_uint(x0); v[4 * j + 1] = __float_as_uint(x1);
+      v[4 * j + 2] = __float_as_uint(x2); v[4 * j + 3] = __float_as_uint(x3);
+    }
+    tmem_st_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
+    __syncwarp();   // every lane has consumed this residual buffer before lane 0 refills it (next-next chunk)
+  }
+  tmem_st_wait();
+  const float mean = sum * inv_n;
+  float sq = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
+    tmem_ld_wait_dep(v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = __uint_as_float(v[j]) - mean;
+      sq = fmaf(d, d, sq);
+    }
+  }
+  const float rstd = rsqrtf(sq * inv_n + g.ln_eps);
+  uint8_t* bbuf = ring_bf16;   // two 2 KB bf16 staging buffers of this warp inside the idle stage ring
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
+    tmem_ld_wait_dep(v);
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 gm = *reinterpret_cast<const float4*>(gamma_s + k * 32 + 4 * j);
+      const float4 bt = *reinterpret_cast<const float4*>(beta_s + k * 32 + 4 * j);
+      f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * gm.x + bt.x;
+      f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * gm.y + bt.y;
+      f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * gm.z + bt.z;
+      f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * gm.w + bt.w;
+    }
+    if (lane == 0) bulk_wait_group_read<1>();   // the stores that last used this buffer pair have read it
+    __syncwarp();
+    stage_chunk<EPI_BIAS_F32>(buf2 + (k & 1) * 4096, lane, f);
+    stage_chunk<EPI_BIAS_BF16>(bbuf + (k & 1) * 2048, lane, f);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmX, buf2 + (k & 1) * 4096, k * 32, row0);
+      tma_store_2d(tmXb, bbuf + (k & 1) * 2048, k * 32, row0);
+      bulk_commit_group();
+    }
+  }
+  if (lane == 0) bulk_wait_group<0>();
+}
+
 template <int KC>
 __device__ __forceinline__ void epi_store_candidates(const GemmArgs& g, int half, int row, const TopK<KC>& top) {
   if (row < g.M) {
@@ -276,7 +377,7 @@ __device__ __forceinline__ void epi_store_candidates(const GemmArgs& g, int half
 template <int BN, int EPI, int KC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
@@ -284,14 +385,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // keep the pointer arithmetic on the __shared__ array itself so accesses stay in the shared window
   // (LDS/STS) instead of degrading to generic loads; SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stg_all = tiles + STAGES * Cfg::STAGE_BYTES;                    // [8 warps][2][STG_BYTES], 1024-aligned
-  uint8_t* tail = stg_all + kEpiWarps * 2 * Cfg::STG_BYTES;
+  uint8_t* stg_all = tiles + STAGES * Cfg::STAGE_BYTES;                    // per-warp staging buffers, 1024-aligned
+  uint8_t* tail = stg_all + Cfg::STG_TOTAL;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* bias_smem = reinterpret_cast<float*>(tail + 256);   // [2][BN]
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);  // EPI_RES_LN: [4 warps][2] residual-tile barriers
+  float* bias_smem = reinterpret_cast<float*>(tail + 512);   // [2][BN]  (EPI_RES_LN: bias | gamma | beta, 2*BN each)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -305,8 +407,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if constexpr (EPI != EPI_TOPK) tma_prefetch_desc(&tmC);
+    if constexpr (EPI == EPI_RES_LN) tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
+    if constexpr (EPI == EPI_RES_LN) for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -362,6 +466,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         umma_commit(&tfull[buf]);  // accumulator complete
       }
+    }
+  } else if constexpr (EPI == EPI_RES_LN) {
+    // ---------------- fused residual + LayerNorm epilogue: warps 2..5, one per TMEM lane quadrant ----------------
+    if (warp < 6) {
+      const int q = warp & 3;
+      const int row0 = m_blk * BM + q * 32;
+      float* gamma_s = bias_smem + 2 * BN;
+      float* beta_s = bias_smem + 4 * BN;
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) {
+        bias_smem[i] = g.bias ? __ldg(g.bias + i) : 0.f;
+        gamma_s[i] = __ldg(g.gamma + i);
+        beta_s[i] = __ldg(g.beta + i);
+      }
+      named_bar_sync(1, 128);
+      epi_res_ln<BN>(g, &tmC, &tmD, tmem_base + (static_cast<uint32_t>(q * 32) << 16), tfull, rbar + (warp - 2) * 2,
+                     stg_all + (warp - 2) * 2 * 4096, tiles + (warp - 2) * 4096, bias_smem, gamma_s, beta_s, lane, row0);
     }
   } else {
     // ---------------- epilogue (warps 2..9): two warps per TMEM lane quadrant ----------------
@@ -427,7 +547,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint64_t* tempty = tfull + 2;
   uint64_t* afull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-  float* bias_smem = reinterpret_cast<float*>(tail + 256);   // [2][BN]
+  float* bias_smem = reinterpret_cast<float*>(tail + 512);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
