@@ -40,7 +40,7 @@ def load_peaks() -> tuple[dict, str]:
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU every 20 ms while the timed region runs."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def finish(self) -> dict:
         self._stop_evt.set()

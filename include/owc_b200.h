@@ -154,6 +154,15 @@ int32_t owc_score(owc_encoder* enc, const int32_t* ids, int32_t ids_space, const
  * selects the tcgen05 column-tile width (128, 192 or 256; 0 = the encoder's default).            */
 int32_t owc_debug_gemm(owc_ctx* ctx, const float* a, const float* w, const float* bias, int32_t m,
                        int32_t n, int32_t kdim, int32_t precision, int32_t tile_n, float* c);
+/* Debug: run the 1-CTA tcgen05 kernel once on an m x n x kdim problem (bf16 output + bias epilogue;
+ * gelu != 0 adds the GELU) on zero-filled operands and return per-CTA clock64 stamps, 8 int64 per CTA
+ * (grid = ceil(m/128) CTAs): [0] entry, [1] setup done, [2] first operands landed, [3] last MMA issued,
+ * [4] first accumulator ready, [5] epilogue done, [6] all warps done, [7] globaltimer (ns) at entry.  */
+int32_t owc_debug_gemm_timeline(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int64_t* stamps,
+                                int32_t max_ctas);
+/* Debug: CUDA-event time of `iters` back-to-back launches of the same 1-CTA kernel (ms per launch). */
+int32_t owc_debug_gemm_loop(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int32_t iters,
+                            float* ms_per_launch);
 /* Time `iters` back-to-back launches of the fused similarity+top-k kernel alone on bf16 operands
  * already resident in device memory (CUDA events on the ctx stream); ms_per_launch out.          */
 int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, int32_t k, int32_t iters,

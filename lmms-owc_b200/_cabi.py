@@ -60,6 +60,8 @@ EXPORTS = {
     "owc_sim_topk": (_I32, [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "owc_score": (_I32, [_P, _P, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32]),
     "owc_debug_gemm": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "owc_debug_gemm_timeline": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32]),
+    "owc_debug_gemm_loop": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_bench_sim_kernel": (_I32, [_P, _I64, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
 }
 

@@ -68,6 +68,8 @@ struct owc_ctx {
   int gemm_mode = 0;       // encoder contractions (env OWC_GEMM_MODE)
   int sim_mode = 2;        // similarity + top-k     (env OWC_SIM_MODE)
   int fuse_ln = 1;         // fuse residual+LayerNorm into the O-proj / FFN2 epilogue (env OWC_FUSE_LN)
+  int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
+  int pdl = 1;             // programmatic dependent launch between the kernels of a layer (env OWC_PDL)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -211,13 +213,13 @@ static int check_gemm_shape(const GemmArgs& g, int epi) {
   return 0;
 }
 
-template <int BN, int EPI, int KC>
-static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
-                          int splits, const CUtensorMap* td = nullptr) {
-  using Cfg = GemmCfg<BN, EPI>;
+template <int BN, int EPI, int KC, bool ARES>
+static int launch_gemm_tc_impl(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
+                               int splits, const CUtensorMap* td) {
+  using Cfg = GemmCfg<BN, EPI, ARES>;
   static bool attr_done = false;
   if (!attr_done) {
-    CU_OK(cudaFuncSetAttribute(k_gemm_tc<BN, EPI, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CU_OK(cudaFuncSetAttribute(k_gemm_tc<BN, EPI, KC, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   OWC_TRY(check_gemm_shape(g, EPI));
@@ -229,8 +231,33 @@ static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& 
   ProfScope prof(c, EPI == EPI_TOPK ? OWC_KCAT_SIM : OWC_KCAT_GEMM);
   if (EPI == EPI_RES_LN && (g.N != 2 * BN || gy != 1 || !td || !g.gamma || !g.beta))
     return fail("fused LayerNorm epilogue needs N == %d and whole rows per CTA", 2 * BN);
-  k_gemm_tc<BN, EPI, KC><<<grid, kGemmThreads, Cfg::SMEM_BYTES, c->stream>>>(ta, tb, tc, td ? *td : tc, g);
+  // Programmatic dependent launch: this kernel's CTAs may be scheduled (and run their prologue: TMEM
+  // allocation, barrier init, descriptor prefetch) while the previous kernel in the stream drains;
+  // griddepcontrol.wait inside the kernel orders every dependent global access.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, EPI, KC, ARES>, ta, tb, tc, td ? *td : tc, g));
   return check_launch(c, "k_gemm_tc");
+}
+
+// 1-CTA kernel; the A block stays resident in shared memory when it fits (K <= 384) unless OWC_ARES=0.
+template <int BN, int EPI, int KC>
+static int launch_gemm_tc(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
+                          int splits, const CUtensorMap* td = nullptr) {
+  // only where at least three W stages still fit next to the 96 KB resident block
+  constexpr int ares_stages = (kSmemLimit - epi_fixed_bytes(BN, EPI) - 6 * 128 * 64 * 2) / (BN * 64 * 2);
+  if constexpr (ares_stages >= 3) {
+    if (c->ares && g.K <= kAresMaxK) return launch_gemm_tc_impl<BN, EPI, KC, true>(c, ta, tb, tc, g, splits, td);
+  }
+  return launch_gemm_tc_impl<BN, EPI, KC, false>(c, ta, tb, tc, g, splits, td);
 }
 
 // CTA-pair kernel: `tb_half` is the W tensor map with a BN/2-row box (each CTA stages half a tile).
@@ -327,6 +354,8 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* gm = getenv("OWC_GEMM_MODE")) c->gemm_mode = std::max(0, std::min(2, atoi(gm)));
   if (const char* sm = getenv("OWC_SIM_MODE")) c->sim_mode = std::max(0, std::min(2, atoi(sm)));
   if (const char* fl = getenv("OWC_FUSE_LN")) c->fuse_ln = atoi(fl) != 0;
+  if (const char* ar = getenv("OWC_ARES")) c->ares = atoi(ar) != 0;
+  if (const char* pd = getenv("OWC_PDL")) c->pdl = atoi(pd) != 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -579,7 +608,17 @@ static int launch_attn_mma(owc_encoder* e, const AttnArgs& aa) {
     const int per_sm = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));                             \
     const long long want = (pairs + 3) / 4;                                                                 \
     const unsigned grid = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(c->sm_count) * per_sm)); \
-    k_attn_mma<DD, TP><<<grid, 128, smem, c->stream>>>(aa);                                                 \
+    cudaLaunchConfig_t cfg{};                                                                               \
+    cfg.gridDim = dim3(grid);                                                                               \
+    cfg.blockDim = dim3(128);                                                                               \
+    cfg.dynamicSmemBytes = smem;                                                                            \
+    cfg.stream = c->stream;                                                                                 \
+    cudaLaunchAttribute attr[1];                                                                            \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+    attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;                                    \
+    cfg.attrs = attr;                                                                                       \
+    cfg.numAttrs = 1;                                                                                       \
+    CU_OK(cudaLaunchKernelEx(&cfg, k_attn_mma<DD, TP>, aa));                                                \
   } while (0)
   if (D == 32) {
     if (aa.max_t <= 16) ATTN_MMA_LAUNCH(32, 16);
@@ -992,6 +1031,72 @@ extern "C" int32_t owc_debug_gemm(owc_ctx* c, const float* a, const float* w, co
     default: return fail("tile_n must be 128, 192 or 256 (+1000: CTA pair, +2000: CTA pair with resident A)");
   }
 #undef DBG_CASE
+}
+
+extern "C" int32_t owc_debug_gemm_timeline(owc_ctx* c, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int64_t* stamps,
+                                           int32_t max_ctas) {
+  if (!c || !stamps) return fail("owc_debug_gemm_timeline: NULL argument");
+  if (m <= 0 || n <= 0 || kdim <= 0 || n % kEncBN != 0) return fail("owc_debug_gemm_timeline: bad shape (n must be a multiple of %d)", kEncBN);
+  CU_OK(cudaSetDevice(c->device));
+  const int ctas = (m + 127) / 128;
+  if (ctas > max_ctas) return fail("stamps buffer too small: need %d CTAs", ctas);
+  OWC_TRY(ensure(c, c->tmp_a, static_cast<size_t>(m) * kdim * 2));
+  OWC_TRY(ensure(c, c->tmp_b, static_cast<size_t>(n) * kdim * 2));
+  OWC_TRY(ensure(c, c->tmp_c, static_cast<size_t>(m) * n * 2));
+  OWC_TRY(ensure(c, c->tmp_d, static_cast<size_t>(ctas) * 8 * sizeof(long long)));
+  CU_OK(cudaMemsetAsync(c->tmp_a.p, 0, static_cast<size_t>(m) * kdim * 2, c->stream));
+  CU_OK(cudaMemsetAsync(c->tmp_b.p, 0, static_cast<size_t>(n) * kdim * 2, c->stream));
+  CU_OK(cudaMemsetAsync(c->tmp_d.p, 0, static_cast<size_t>(ctas) * 8 * sizeof(long long), c->stream));
+  CUtensorMap ta, tb, tc;
+  OWC_TRY(make_tmap(c, &ta, c->tmp_a.p, m, kdim, 128));
+  OWC_TRY(make_tmap(c, &tb, c->tmp_b.p, n, kdim, kEncBN));
+  OWC_TRY(make_out_tmap(c, &tc, c->tmp_c.p, m, n, true));
+  GemmArgs g{};
+  g.M = m; g.N = n; g.K = kdim;
+  g.dbg = static_cast<long long*>(c->tmp_d.p);
+  for (int rep = 0; rep < 3; ++rep) {   // the last (warm) launch's stamps are returned
+    if (gelu) OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, ta, tb, tc, g, 1)));
+    else OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, ta, tb, tc, g, 1)));
+  }
+  CU_OK(cudaMemcpyAsync(stamps, c->tmp_d.p, static_cast<size_t>(ctas) * 8 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int32_t owc_debug_gemm_loop(owc_ctx* c, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int32_t iters,
+                                       float* ms_per_launch) {
+  if (!c || !ms_per_launch || iters <= 0) return fail("owc_debug_gemm_loop: bad argument");
+  if (m <= 0 || n <= 0 || kdim <= 0 || n % kEncBN != 0) return fail("owc_debug_gemm_loop: bad shape");
+  CU_OK(cudaSetDevice(c->device));
+  OWC_TRY(ensure(c, c->tmp_a, static_cast<size_t>(m) * kdim * 2));
+  OWC_TRY(ensure(c, c->tmp_b, static_cast<size_t>(n) * kdim * 2));
+  OWC_TRY(ensure(c, c->tmp_c, static_cast<size_t>(m) * n * 2));
+  CU_OK(cudaMemsetAsync(c->tmp_a.p, 0, static_cast<size_t>(m) * kdim * 2, c->stream));
+  CU_OK(cudaMemsetAsync(c->tmp_b.p, 0, static_cast<size_t>(n) * kdim * 2, c->stream));
+  CUtensorMap ta, tb, tc;
+  OWC_TRY(make_tmap(c, &ta, c->tmp_a.p, m, kdim, 128));
+  OWC_TRY(make_tmap(c, &tb, c->tmp_b.p, n, kdim, kEncBN));
+  OWC_TRY(make_out_tmap(c, &tc, c->tmp_c.p, m, n, true));
+  GemmArgs g{};
+  g.M = m; g.N = n; g.K = kdim;
+  auto run = [&]() -> int {
+    if (gelu) return launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, ta, tb, tc, g, 1);
+    return launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, ta, tb, tc, g, 1);
+  };
+  for (int i = 0; i < 3; ++i) OWC_TRY(run());
+  cudaEvent_t e0, e1;
+  CU_OK(cudaEventCreate(&e0));
+  CU_OK(cudaEventCreate(&e1));
+  CU_OK(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) OWC_TRY(run());
+  CU_OK(cudaEventRecord(e1, c->stream));
+  CU_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return 0;
 }
 
 __global__ void k_fill_unit_bf16(__nv_bfloat16* p, long long rows, int dim, unsigned seed) {

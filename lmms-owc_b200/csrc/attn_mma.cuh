@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(128) k_attn_mma(const AttnArgs a) {
   for (int i = lane; i < Cfg::region_elems(TPMAX) / 8; i += 32) reinterpret_cast<uint4*>(reg)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
 
+  pdl_launch_dependents();
+  pdl_wait();   // the QKV projections of this chunk are complete and visible
+
   const float scale_log2 = a.scale * 1.4426950408889634f;
   const long long pairs = static_cast<long long>(a.n_seq) * a.heads;
   const long long stride = static_cast<long long>(gridDim.x) * 4;

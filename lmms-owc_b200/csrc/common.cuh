@@ -54,6 +54,50 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-h, e, fmaf(0.5f, x, h));
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2): two elements per issue slot.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_fast on a pair, polynomial in packed arithmetic (cubic q, |erf error| 1.5e-5: still two orders
+// below the bf16 rounding of the result): gelu(x) = relu(x) - 0.5|x| * 2^(-z q(z)), z = min(|x|/sqrt2, 4).
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.0f);
+  const float z1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.0f);
+  const uint64_t z = f2_pack(z0, z1);
+  uint64_t p = f2_fma(f2_pack(-0.0191262871f, -0.0191262871f), z, f2_pack(0.136623386f, 0.136623386f));
+  p = f2_fma(p, z, f2_pack(0.923601230f, 0.923601230f));
+  p = f2_fma(p, z, f2_pack(1.62727115f, 1.62727115f));
+  p = f2_mul(p, z);
+  float p0, p1, e0, e1;
+  f2_unpack(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-p0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-p1));
+  const uint64_t r = f2_fma(f2_pack(fabsf(x0) * -0.5f, fabsf(x1) * -0.5f), f2_pack(e0, e1),
+                            f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  f2_unpack(r, x0, x1);
+}
+
+// Programmatic dependent launch (PDL). launch_dependents: the next kernel in the stream may start being
+// scheduled; wait: block until the previous kernel has completed and its writes are visible. Both are
+// no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

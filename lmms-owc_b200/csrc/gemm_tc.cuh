@@ -49,6 +49,7 @@ struct GemmArgs {
   const float* gamma;      // EPI_RES_LN: LayerNorm weight / bias [N] and epsilon
   const float* beta;
   float ln_eps;
+  long long* dbg;          // optional per-CTA timeline stamps [cta][8] (clock64), nullptr in production
 };
 
 constexpr int kEpiWarps = 8;
@@ -67,18 +68,23 @@ __host__ __device__ constexpr int epi_fixed_bytes(int bn, int epi) {
 }
 __host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
 
-template <int BN, int EPI>
+// ARES: the CTA's whole A block (128 x K, K <= 384) is loaded once and stays resident, so a stage only
+// carries the W tile. The kernel is shared-memory-bandwidth bound (every k-block is written by TMA and
+// read by the tensor core: 2 x 40 KB at BN = 192 against ~128 B/clk), so dropping the A refills of
+// every column tile is a direct 20 % cut of the per-k-block traffic.
+template <int BN, int EPI, bool ARES = false>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI)) / STAGE_BYTES);
+  static constexpr int STAGE_BYTES = (ARES ? 0 : A_BYTES) + B_BYTES;
+  static constexpr int ARES_BYTES = ARES ? 6 * A_BYTES : 0;
+  static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI) - ARES_BYTES) / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int STG_BYTES = epi_stage_bytes(EPI);
   static constexpr int STG_TOTAL = (EPI == EPI_RES_LN) ? 4 * 2 * 4096 : kEpiWarps * 2 * STG_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
+  static constexpr int SMEM_BYTES = ARES_BYTES + STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -239,7 +245,7 @@ __device__ __forceinline__ void epi_process(const GemmArgs& g, const CUtensorMap
       }
       if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+        for (int j = 0; j < 32; j += 2) gelu_fast2(f[j], f[j + 1]);
       }
       if constexpr (EPI == EPI_BIAS_RES_F32) {
         if (row < g.M) {
@@ -374,24 +380,26 @@ __device__ __forceinline__ void epi_store_candidates(const GemmArgs& g, int half
 // ------------------------------------------------------------------------------------------------
 // one CTA per 128 rows
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int KC>
+template <int BN, int EPI, int KC, bool ARES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BN, EPI, ARES>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer arithmetic on the __shared__ array itself so accesses stay in the shared window
   // (LDS/STS) instead of degrading to generic loads; SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ares = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // resident A block (ARES)
+  uint8_t* tiles = ares + Cfg::ARES_BYTES;
   uint8_t* stg_all = tiles + STAGES * Cfg::STAGE_BYTES;                    // per-warp staging buffers, 1024-aligned
   uint8_t* tail = stg_all + Cfg::STG_TOTAL;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
   uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);  // EPI_RES_LN: [4 warps][2] residual-tile barriers
   float* bias_smem = reinterpret_cast<float*>(tail + 512);   // [2][BN]  (EPI_RES_LN: bias | gamma | beta, 2*BN each)
 
@@ -402,6 +410,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int tile0 = blockIdx.y * g.tiles_per_cta;
   const int tile1 = min(tile0 + g.tiles_per_cta, tiles_total);
   const int num_kb = g.K / BK;
+  long long* dbg = g.dbg ? g.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define OWC_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0 && dbg) {
+    dbg[0] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[7] = gt;
+  }
 
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -411,6 +427,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
     if constexpr (EPI == EPI_RES_LN) for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
+    mbar_init(afull, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -421,10 +438,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) OWC_STAMP(1);
+  pdl_launch_dependents();   // the next kernel may begin its own prologue
+  pdl_wait();                // everything below reads what the previous kernel wrote
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
+      if constexpr (ARES) {   // the row block's A operand, all k-blocks, once
+        mbar_expect_tx(afull, static_cast<uint32_t>(num_kb) * Cfg::A_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(ares + kb * Cfg::A_BYTES, &tmA, afull, kb * BK, m_blk * BM);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
@@ -432,8 +456,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, tile * BN);
+          if constexpr (!ARES) {
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+            sa += Cfg::A_BYTES;
+          }
+          tma_load_2d(sa, &tmB, &full[stage], kb * BK, tile * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -442,6 +469,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      if constexpr (ARES) {
+        mbar_wait(afull, 0);
+        tc_fence_after();
+      }
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -453,9 +484,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (t == 0 && kb == 0) OWC_STAMP(2);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t s_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = ARES ? smem_u32(ares + kb * Cfg::A_BYTES) : s_addr;
+          const uint32_t b_addr = ARES ? s_addr : s_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_f16(d_tmem, make_sw128_kmajor_desc(a_addr + k * 32), make_sw128_kmajor_desc(b_addr + k * 32),
@@ -466,6 +499,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         umma_commit(&tfull[buf]);  // accumulator complete
       }
+      OWC_STAMP(3);
     }
   } else if constexpr (EPI == EPI_RES_LN) {
     // ---------------- fused residual + LayerNorm epilogue: warps 2..5, one per TMEM lane quadrant ----------------
@@ -499,6 +533,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       float* bias_s = bias_smem + buf * BN;
       epi_stage_bias<BN, EPI>(g, tile, bias_s);
       mbar_wait(&tfull[buf], use & 1);
+      if (t == 0 && threadIdx.x == 64) OWC_STAMP(4);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       epi_process<BN, EPI, KC>(g, &tmC, tile, tbase, bias_s, stg, half, lane, row0, store_count, top);
@@ -506,12 +541,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+    if (threadIdx.x == 64) OWC_STAMP(5);
     if constexpr (EPI == EPI_TOPK) epi_store_candidates<KC>(g, half, row0 + lane, top);
     else if (lane == 0) bulk_wait_group<0>();   // staged tiles fully written before the CTA retires
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) OWC_STAMP(6);
+#undef OWC_STAMP
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
