@@ -686,7 +686,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
       g = GemmArgs{};
       g.M = M; g.N = H; g.K = H; g.bias = L.bo;
       if (fuse_ln) {
-        g.gamma = L.ln1g; g.beta = L.ln1b; g.ln_eps = a.ln_eps;
+        g.gamma = L.ln1g; g.beta = L.ln1b; g.ln_eps = a.ln_eps; g.residual = e->x; g.ldo = H;
         OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_ao, L.tm_wo, e->tmo_x, g, 1, &e->tmo_xb)));
       } else {
         g.residual = e->x; g.ldo = H;
@@ -713,7 +713,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
       g = GemmArgs{};
       g.M = M; g.N = H; g.K = I; g.bias = L.b2;
       if (fuse_ln) {
-        g.gamma = L.ln2g; g.beta = L.ln2b; g.ln_eps = a.ln_eps;
+        g.gamma = L.ln2g; g.beta = L.ln2b; g.ln_eps = a.ln_eps; g.residual = e->x; g.ldo = H;
         OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_f, L.tm_w2, e->tmo_x, g, 1, &e->tmo_xb)));
       } else {
         g.residual = e->x; g.ldo = H;
@@ -1054,8 +1054,20 @@ extern "C" int32_t owc_debug_gemm_timeline(owc_ctx* c, int32_t m, int32_t n, int
   GemmArgs g{};
   g.M = m; g.N = n; g.K = kdim;
   g.dbg = static_cast<long long*>(c->tmp_d.p);
+  CUtensorMap tx;
+  if (gelu == 2) {   // fused residual + LayerNorm epilogue: needs n == 2 * kEncBN, an fp32 x and gamma/beta
+    if (n != 2 * kEncBN) return fail("LayerNorm timeline needs n == %d", 2 * kEncBN);
+    OWC_TRY(ensure(c, c->zc32, static_cast<size_t>(m) * n * sizeof(float)));
+    OWC_TRY(ensure(c, c->zp, 3 * static_cast<size_t>(n) * sizeof(float)));
+    CU_OK(cudaMemsetAsync(c->zc32.p, 0, static_cast<size_t>(m) * n * sizeof(float), c->stream));
+    CU_OK(cudaMemsetAsync(c->zp.p, 0, 3 * static_cast<size_t>(n) * sizeof(float), c->stream));
+    OWC_TRY(make_out_tmap(c, &tx, c->zc32.p, m, n, false));
+    g.residual = static_cast<const float*>(c->zc32.p); g.ldo = n;
+    g.gamma = static_cast<const float*>(c->zp.p); g.beta = g.gamma + n; g.bias = g.gamma + 2 * n; g.ln_eps = 1e-12f;
+  }
   for (int rep = 0; rep < 3; ++rep) {   // the last (warm) launch's stamps are returned
-    if (gelu) OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, ta, tb, tc, g, 1)));
+    if (gelu == 2) OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, ta, tb, tx, g, 1, &tc)));
+    else if (gelu) OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, ta, tb, tc, g, 1)));
     else OWC_TRY((launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, ta, tb, tc, g, 1)));
   }
   CU_OK(cudaMemcpyAsync(stamps, c->tmp_d.p, static_cast<size_t>(ctas) * 8 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1079,7 +1091,19 @@ extern "C" int32_t owc_debug_gemm_loop(owc_ctx* c, int32_t m, int32_t n, int32_t
   OWC_TRY(make_out_tmap(c, &tc, c->tmp_c.p, m, n, true));
   GemmArgs g{};
   g.M = m; g.N = n; g.K = kdim;
+  CUtensorMap tx;
+  if (gelu == 2) {
+    if (n != 2 * kEncBN) return fail("LayerNorm loop needs n == %d", 2 * kEncBN);
+    OWC_TRY(ensure(c, c->zc32, static_cast<size_t>(m) * n * sizeof(float)));
+    OWC_TRY(ensure(c, c->zp, 3 * static_cast<size_t>(n) * sizeof(float)));
+    CU_OK(cudaMemsetAsync(c->zc32.p, 0, static_cast<size_t>(m) * n * sizeof(float), c->stream));
+    CU_OK(cudaMemsetAsync(c->zp.p, 0, 3 * static_cast<size_t>(n) * sizeof(float), c->stream));
+    OWC_TRY(make_out_tmap(c, &tx, c->zc32.p, m, n, false));
+    g.residual = static_cast<const float*>(c->zc32.p); g.ldo = n;
+    g.gamma = static_cast<const float*>(c->zp.p); g.beta = g.gamma + n; g.bias = g.gamma + 2 * n; g.ln_eps = 1e-12f;
+  }
   auto run = [&]() -> int {
+    if (gelu == 2) return launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, ta, tb, tx, g, 1, &tc);
     if (gelu) return launch_gemm_tc<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, ta, tb, tc, g, 1);
     return launch_gemm_tc<kEncBN, EPI_BIAS_BF16, 1>(c, ta, tb, tc, g, 1);
   };

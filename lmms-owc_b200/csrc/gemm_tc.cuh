@@ -63,7 +63,7 @@ __host__ __device__ constexpr int epi_stage_bytes(int epi) {
 }
 __host__ __device__ constexpr int epi_fixed_bytes(int bn, int epi) {
   // EPI_RES_LN: 4 epilogue warps x 2 residual/staging buffers of 4 KB, and bias|gamma|beta of a whole row (2*bn each)
-  return epi == EPI_RES_LN ? 1024 + 512 + 3 * 2 * bn * 4 + 4 * 2 * 4096
+  return epi == EPI_RES_LN ? 1024 + 512 + 3 * 2 * bn * 4 + (kEpiWarps * 4096 + 2048)
                            : 1024 /*align slack*/ + 512 /*barriers*/ + 2 * bn * 4 /*bias*/ + kEpiWarps * 2 * epi_stage_bytes(epi);
 }
 __host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
@@ -83,7 +83,8 @@ struct GemmCfg {
   static constexpr int STAGES = imin(8, (kSmemLimit - epi_fixed_bytes(BN, EPI) - ARES_BYTES) / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int STG_BYTES = epi_stage_bytes(EPI);
-  static constexpr int STG_TOTAL = (EPI == EPI_RES_LN) ? 4 * 2 * 4096 : kEpiWarps * 2 * STG_BYTES;
+  // EPI_RES_LN: a 4 KB transpose scratch per epilogue warp + the 2 KB row-statistics exchange area
+  static constexpr int STG_TOTAL = (EPI == EPI_RES_LN) ? kEpiWarps * 4096 + 2048 : kEpiWarps * 2 * STG_BYTES;
   static constexpr int SMEM_BYTES = ARES_BYTES + STAGES * STAGE_BYTES + epi_fixed_bytes(BN, EPI);
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
@@ -273,94 +274,106 @@ __device__ __forceinline__ void epi_process(const GemmArgs& g, const CUtensorMap
   }
 }
 
-// Fused residual + LayerNorm epilogue (EPI_RES_LN): N == 2*BN, so a row-block's whole rows sit in the
-// two TMEM accumulator buffers and thread r owns row r end to end - the statistics need no cross-
-// thread traffic at all. Executed by ONE warp per TMEM lane quadrant (warps 2..5).
-//   pass 1  v = acc + bias + residual: residual tiles (32x32 fp32) stream in by TMA, double-buffered
-//           in this warp's two 4 KB buffers; v is written back to TMEM (tcgen05.st); row sum
-//   pass 2  re-read TMEM: sum of (v - mean)^2  (two-pass variance, like nn.LayerNorm)
-//   pass 3  re-read TMEM: y = (v - mean) * rstd * gamma + beta -> fp32 tile staged in the same two
-//           buffers and TMA-stored over the residual (x is updated in place), bf16 tile staged in the
-//           (by now idle) pipeline ring and TMA-stored to the operand copy
+// Fused residual + LayerNorm epilogue (EPI_RES_LN): N == 2*BN, so a row block's whole rows sit in the
+// two TMEM accumulator buffers and thread r owns row r. All 8 epilogue warps take part; the two warps
+// of a lane quadrant split the row's 32-column chunks (even / odd) and exchange their partial row
+// statistics through shared memory.
+//   pass A    as each accumulator completes: v = acc + bias + residual for the own chunks. The 32x32
+//             fp32 residual tiles are fetched with coalesced 16-byte loads, prefetched one chunk ahead
+//             in registers (the first one before the accumulator is even ready), and transposed to
+//             row-per-thread through a 4 KB per-warp scratch; v goes back to TMEM (tcgen05.st) and
+//             feeds the row sum / sum of squares. Tile 0's pass A overlaps tile 1's MMAs.
+//   pass B    y = (v - mean) * rstd * gamma + beta -> fp32 tile TMA-stored over the residual (x is
+//             updated in place) and bf16 tile TMA-stored to the operand copy; staging lives in the
+//             operand memory, which is idle by then.
 template <int BN>
-__device__ __forceinline__ void epi_res_ln(const GemmArgs& g, const CUtensorMap* tmX, const CUtensorMap* tmXb,
-                                           uint32_t tmem_q, uint64_t* tfull, uint64_t* rbar, uint8_t* buf2,
-                                           uint8_t* ring_bf16, const float* bias_s, const float* gamma_s,
-                                           const float* beta_s, int lane, int row0) {
-  constexpr int NC = 2 * BN / 32;   // 32-column chunks of a whole row
-  const int sw = lane & 7;
+__device__ __forceinline__ void ln_finish(const GemmArgs& g, const CUtensorMap* tmX, const CUtensorMap* tmXb,
+                                          uint32_t tmem_q, uint64_t* tfull, float* stat_s, uint8_t* scratch,
+                                          uint8_t* stg, const float* bias_s, const float* gamma_s,
+                                          const float* beta_s, int warp_e, int q, int half, int lane, int row0) {
+  constexpr int NCW = 2 * BN / 64;   // chunks per warp: NCW/2 in each accumulator buffer
   const float inv_n = 1.0f / static_cast<float>(2 * BN);
-  if (lane == 0) {
-    mbar_expect_tx(&rbar[0], 4096);
-    tma_load_2d(buf2, tmX, &rbar[0], 0, row0);
-  }
-  float sum = 0.f;
-  uint32_t v[32];
-#pragma unroll 1
-  for (int k = 0; k < NC; ++k) {
-    if (k == 0) { mbar_wait(&tfull[0], 0); tc_fence_after(); }
-    if (k == NC / 2) { mbar_wait(&tfull[1], 0); tc_fence_after(); }
-    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
-    if (lane == 0 && k + 1 < NC) {   // prefetch the next residual tile into the other buffer
-      mbar_expect_tx(&rbar[(k + 1) & 1], 4096);
-      tma_load_2d(buf2 + ((k + 1) & 1) * 4096, tmX, &rbar[(k + 1) & 1], (k + 1) * 32, row0);
+  const int lr = lane >> 3, lc = lane & 7;
+  uint32_t v[2][32];
+  float4 pre[8];
+  auto fetch = [&](int k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + lr + 4 * i;
+      pre[i] = (row < g.M) ? __ldg(reinterpret_cast<const float4*>(g.residual + static_cast<size_t>(row) * g.ldo + k * 32) + lc)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    mbar_wait(&rbar[k & 1], static_cast<uint32_t>((k >> 1) & 1));
-    const uint8_t* rrow = buf2 + (k & 1) * 4096 + lane * 128;
-    tmem_ld_wait_dep(v);
+  };
+  // ---- pass A ----
+  float sum = 0.f, sq = 0.f;
+  fetch(half);
+#pragma unroll 1
+  for (int cw = 0; cw < NCW; ++cw) {
+    const int k = 2 * cw + half;
+    if (cw == 0) { mbar_wait(&tfull[0], 0); tc_fence_after(); }
+    if (cw == NCW / 2) { mbar_wait(&tfull[1], 0); tc_fence_after(); }
+    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v[0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = lr + 4 * i;
+      *reinterpret_cast<float4*>(scratch + r * 128 + ((lc ^ (r & 7)) << 4)) = pre[i];
+    }
+    __syncwarp();
+    if (cw + 1 < NCW) fetch(k + 2);   // next tile's residual flies while this chunk is processed
+    const uint8_t* rrow = scratch + lane * 128;
+    tmem_ld_wait_dep(v[0]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 r = *reinterpret_cast<const float4*>(rrow + ((j ^ sw) << 4));
+      const float4 r = *reinterpret_cast<const float4*>(rrow + ((j ^ (lane & 7)) << 4));
       const float4 b = *reinterpret_cast<const float4*>(bias_s + k * 32 + 4 * j);
-      const float x0 = __uint_as_float(v[4 * j + 0]) + b.x + r.x;
-      const float x1 = __uint_as_float(v[4 * j + 1]) + b.y + r.y;
-      const float x2 = __uint_as_float(v[4 * j + 2]) + b.z + r.z;
-      const float x3 = __uint_as_float(v[4 * j + 3]) + b.w + r.w;
+      const float x0 = __uint_as_float(v[0][4 * j + 0]) + b.x + r.x;
+      const float x1 = __uint_as_float(v[0][4 * j + 1]) + b.y + r.y;
+      const float x2 = __uint_as_float(v[0][4 * j + 2]) + b.z + r.z;
+      const float x3 = __uint_as_float(v[0][4 * j + 3]) + b.w + r.w;
       sum += (x0 + x1) + (x2 + x3);
-      v[4 * j + 0] = __float_as_uint(x0); v[4 * j + 1] = __float_as_uint(x1);
-      v[4 * j + 2] = __float_as_uint(x2); v[4 * j + 3] = __float_as_uint(x3);
+      sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+      v[0][4 * j + 0] = __float_as_uint(x0); v[0][4 * j + 1] = __float_as_uint(x1);
+      v[0][4 * j + 2] = __float_as_uint(x2); v[0][4 * j + 3] = __float_as_uint(x3);
     }
-    tmem_st_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
-    __syncwarp();   // every lane has consumed this residual buffer before lane 0 refills it (next-next chunk)
+    tmem_st_32x32(tmem_q + static_cast<uint32_t>(k * 32), v[0]);
+    __syncwarp();   // scratch is rewritten by the next iteration
   }
   tmem_st_wait();
+  stat_s[(warp_e * 32 + lane) * 2 + 0] = sum;
+  stat_s[(warp_e * 32 + lane) * 2 + 1] = sq;
+  named_bar_sync(2 + q, 64);   // the two warps that share this lane quadrant
+  sum += stat_s[((warp_e ^ 4) * 32 + lane) * 2 + 0];
+  sq += stat_s[((warp_e ^ 4) * 32 + lane) * 2 + 1];
   const float mean = sum * inv_n;
-  float sq = 0.f;
-#pragma unroll 1
-  for (int k = 0; k < NC; ++k) {
-    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
-    tmem_ld_wait_dep(v);
+  const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + g.ln_eps);
+  // ---- pass B: normalise, stage, TMA-store (fp32 over the residual, bf16 operand copy) ----
+  tmem_ld_32x32(tmem_q + static_cast<uint32_t>(half * 32), v[0]);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = __uint_as_float(v[j]) - mean;
-      sq = fmaf(d, d, sq);
-    }
-  }
-  const float rstd = rsqrtf(sq * inv_n + g.ln_eps);
-  uint8_t* bbuf = ring_bf16;   // two 2 KB bf16 staging buffers of this warp inside the idle stage ring
-#pragma unroll 1
-  for (int k = 0; k < NC; ++k) {
-    tmem_ld_32x32(tmem_q + static_cast<uint32_t>(k * 32), v);
-    tmem_ld_wait_dep(v);
+  for (int cw = 0; cw < NCW; ++cw) {
+    const int k = 2 * cw + half;
+    tmem_ld_wait_dep(v[cw & 1]);
+    if (cw + 1 < NCW) tmem_ld_32x32(tmem_q + static_cast<uint32_t>((k + 2) * 32), v[(cw + 1) & 1]);
     float f[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 gm = *reinterpret_cast<const float4*>(gamma_s + k * 32 + 4 * j);
       const float4 bt = *reinterpret_cast<const float4*>(beta_s + k * 32 + 4 * j);
-      f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * gm.x + bt.x;
-      f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * gm.y + bt.y;
-      f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * gm.z + bt.z;
-      f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * gm.w + bt.w;
+      f[4 * j + 0] = (__uint_as_float(v[cw & 1][4 * j + 0]) - mean) * rstd * gm.x + bt.x;
+      f[4 * j + 1] = (__uint_as_float(v[cw & 1][4 * j + 1]) - mean) * rstd * gm.y + bt.y;
+      f[4 * j + 2] = (__uint_as_float(v[cw & 1][4 * j + 2]) - mean) * rstd * gm.z + bt.z;
+      f[4 * j + 3] = (__uint_as_float(v[cw & 1][4 * j + 3]) - mean) * rstd * gm.w + bt.w;
     }
-    if (lane == 0) bulk_wait_group_read<1>();   // the stores that last used this buffer pair have read it
+    uint8_t* fbuf = stg + (cw & 1) * 4096;          // fp32 tile
+    uint8_t* bbuf = stg + 8192 + (cw & 1) * 2048;   // bf16 tile
+    if (lane == 0) bulk_wait_group_read<1>();       // the stores that last used this buffer pair have read it
     __syncwarp();
-    stage_chunk<EPI_BIAS_F32>(buf2 + (k & 1) * 4096, lane, f);
-    stage_chunk<EPI_BIAS_BF16>(bbuf + (k & 1) * 2048, lane, f);
+    stage_chunk<EPI_BIAS_F32>(fbuf, lane, f);
+    stage_chunk<EPI_BIAS_BF16>(bbuf, lane, f);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmX, buf2 + (k & 1) * 4096, k * 32, row0);
-      tma_store_2d(tmXb, bbuf + (k & 1) * 2048, k * 32, row0);
+      tma_store_2d(tmX, fbuf, k * 32, row0);
+      tma_store_2d(tmXb, bbuf, k * 32, row0);
       bulk_commit_group();
     }
   }
@@ -399,8 +412,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* afull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-  uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);  // EPI_RES_LN: [4 warps][2] residual-tile barriers
+  uint64_t* tinit = afull + 1;                               // EPI_RES_LN: accumulators pre-loaded with residual + bias
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tinit + 1);
   float* bias_smem = reinterpret_cast<float*>(tail + 512);   // [2][BN]  (EPI_RES_LN: bias | gamma | beta, 2*BN each)
 
   const int warp = threadIdx.x >> 5;
@@ -426,7 +439,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if constexpr (EPI == EPI_RES_LN) tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
-    if constexpr (EPI == EPI_RES_LN) for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
+    mbar_init(tinit, kEpiWarps);
     mbar_init(afull, 1);
     fence_barrier_init();
   }
@@ -502,21 +515,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       OWC_STAMP(3);
     }
   } else if constexpr (EPI == EPI_RES_LN) {
-    // ---------------- fused residual + LayerNorm epilogue: warps 2..5, one per TMEM lane quadrant ----------------
-    if (warp < 6) {
-      const int q = warp & 3;
-      const int row0 = m_blk * BM + q * 32;
-      float* gamma_s = bias_smem + 2 * BN;
-      float* beta_s = bias_smem + 4 * BN;
-      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) {
-        bias_smem[i] = g.bias ? __ldg(g.bias + i) : 0.f;
-        gamma_s[i] = __ldg(g.gamma + i);
-        beta_s[i] = __ldg(g.beta + i);
-      }
-      named_bar_sync(1, 128);
-      epi_res_ln<BN>(g, &tmC, &tmD, tmem_base + (static_cast<uint32_t>(q * 32) << 16), tfull, rbar + (warp - 2) * 2,
-                     stg_all + (warp - 2) * 2 * 4096, tiles + (warp - 2) * 4096, bias_smem, gamma_s, beta_s, lane, row0);
+    // ---------------- fused residual + LayerNorm epilogue (all 8 epilogue warps) ----------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int warp_e = warp - 2;
+    const int row0 = m_blk * BM + q * 32;
+    const uint32_t tmem_q = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* gamma_s = bias_smem + 2 * BN;
+    float* beta_s = bias_smem + 4 * BN;
+    float* stat_s = reinterpret_cast<float*>(stg_all + kEpiWarps * 4096);   // [8 warps][32 rows][sum, sumsq]
+    for (int i = threadIdx.x - 64; i < 2 * BN; i += kEpiThreads) {
+      bias_smem[i] = g.bias ? __ldg(g.bias + i) : 0.f;
+      gamma_s[i] = __ldg(g.gamma + i);
+      beta_s[i] = __ldg(g.beta + i);
     }
+    named_bar_sync(1, kEpiThreads);
+    // pass-B staging lives at the start of the operand memory (resident A block / stage ring), idle by then
+    ln_finish<BN>(g, &tmC, &tmD, tmem_q, tfull, stat_s, stg_all + warp_e * 4096, ares + warp_e * 12288, bias_smem,
+                  gamma_s, beta_s, warp_e, q, half, lane, row0);
+    if (threadIdx.x == 64) OWC_STAMP(5);
   } else {
     // ---------------- epilogue (warps 2..9): two warps per TMEM lane quadrant ----------------
     const int q = warp & 3;

@@ -205,3 +205,42 @@ def test_concept_metric_matches_reference_golden(oracle_backed, monkeypatch):
 def test_encode_unique_dedups(oracle_backed):
     z, inv = T.encode_unique(["a b", "c", "a b", "c", "d"])
     assert z.shape == (3, 384) and inv.tolist() == [0, 1, 0, 1, 2]
+
+
+def test_eval_metrics_cli_roundtrip(oracle_backed, tmp_path, capsys):
+    """a1: file discovery, item building, JSONL write-back columns and stdout block of eval_metrics.py."""
+    import pandas as pd
+
+    from owc_b200 import eval_metrics as EM
+
+    b = oracle_backed
+    cls = [str(s) for s in b.gold["class_names"]]
+    preds = [str(s) for s in b.gold["preds"]][:40]
+    tg = b.gold["targets"][:40]
+    run = tmp_path / "logs" / "caltech101" / "model-a"
+    run.mkdir(parents=True)
+    rows = [{"doc_id": i, "target": cls[t], "filtered_resps": [p], "resps": [[p]]} for i, (t, p) in enumerate(zip(tg, preds))]
+    f = run / "run_samples_caltech101.jsonl"
+    pd.DataFrame(rows).to_json(f, lines=True, orient="records")
+    # a multi-round file: [[r1, r2]] per row, last round scored
+    run2 = tmp_path / "logs" / "caltech101" / "model-b"
+    run2.mkdir(parents=True)
+    rows2 = [{"doc_id": i, "target": cls[t], "filtered_resps": [["first round", p]]} for i, (t, p) in enumerate(zip(tg, preds))]
+    pd.DataFrame(rows2).to_json(run2 / "x_samples_y.jsonl", lines=True, orient="records")
+
+    args = EM.build_parser().parse_args(["-i", str(tmp_path / "logs"), "-m", "semantic_similarity,mean_average_semantic_similarity"])
+    out = EM.main(args)
+    assert set(out) == {"caltech101"} and set(out["caltech101"]) == {"model-a", "model-b"}
+    gold = b.gold["paired_scores"][:40]
+    assert abs(out["caltech101"]["model-a"]["semantic_similarity"] - float(gold.mean())) < 1e-6
+    assert abs(out["caltech101"]["model-b"]["semantic_similarity"] - float(gold.mean())) < 1e-6
+    df = pd.read_json(f, lines=True)
+    assert np.abs(df["semantic_similarity"].to_numpy(np.float32) - gold).max() < 2e-6
+    for col in ("mean_average_semantic_similarity", "semantic_similarity@0.5", "semantic_similarity@0.9"):
+        assert col in df.columns
+    assert df["semantic_similarity@0.9"].tolist() == (gold >= np.float32(0.9)).astype(int).tolist()
+    text = capsys.readouterr().out
+    assert "Semantic similarity on caltech101:" in text
+    assert f"{'model-a':<29}: {float(gold.mean()):.3f}" in text
+    with pytest.raises(KeyError):
+        EM.score_file(str(f), ["bleu"])

@@ -1,0 +1,141 @@
+"""Row sharding across ranks on CPU: world_size-2 gloo processes with an oracle-backed
+engine standing in for the CUDA engine (tests may use the oracle; the product may not). Checks the
+partition, the class-embedding broadcast, the padded gather and that the sharded result equals the
+single-process result row for row."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import owc_b200  # noqa: F401
+from owc_b200 import sharded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_split_rows_balanced_properties():
+    rng = np.random.default_rng(0)
+    for n, world in [(0, 4), (1, 4), (7, 2), (1000, 8), (1000, 3)]:
+        w = rng.integers(3, 40, n)
+        blocks = sharded.split_rows_balanced(w, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(b[1] == nb[0] for b, nb in zip(blocks, blocks[1:])) and all(b0 <= b1 for b0, b1 in blocks)
+        if n >= 100:
+            loads = [w[b0:b1].sum() for b0, b1 in blocks]
+            assert max(loads) - min(loads) <= 2 * w.max()      # balanced by weight, not by row count
+    assert sharded.split_rows_balanced([5, 5, 5, 5], 2) == [(0, 2), (2, 4)]
+    with pytest.raises(ValueError):
+        sharded.split_rows_balanced([1], 0)
+
+
+class _OracleEngine:
+    """CPU stand-in with the Engine methods the sharding layer uses (encode/score, out='device')."""
+
+    def __init__(self, arch, sd):
+        self.arch, self.sd = arch, sd
+        self.encode_calls = 0
+
+    def _pad(self, ids, cu):
+        n = len(cu) - 1
+        lens = np.diff(cu)
+        t = max(int(lens.max()) if n else 1, 1)
+        ids_p = np.full((n, t), self.arch.pad_id, dtype=np.int64)
+        mask = np.zeros((n, t), dtype=np.int64)
+        for i in range(n):
+            ids_p[i, :lens[i]] = ids[cu[i]:cu[i + 1]]
+            mask[i, :lens[i]] = 1
+        return torch.from_numpy(ids_p), torch.from_numpy(mask)
+
+    def encode(self, ids, cu, out="host", precision=None):
+        from oracle import encoder_ref
+
+        self.encode_calls += 1
+        n = len(cu) - 1
+        if n == 0:
+            return torch.zeros(0, self.arch.hidden)
+        z = encoder_ref.encode_padded(self.sd, self.arch, *self._pad(np.asarray(ids), np.asarray(cu)))
+        return z if out == "device" else z.numpy()
+
+    def score(self, ids, cu, zc, targets=None, k=1, precision=None, out="host", want_embeds=False):
+        from oracle import encoder_ref
+
+        zp = self.encode(ids, cu, out="device")
+        if zp.shape[0] == 0:
+            return {"scores": torch.zeros(0, k), "idx": torch.zeros(0, k, dtype=torch.int32),
+                    "paired": torch.zeros(0) if targets is not None else None, "embeds": None}
+        s, i, _ = encoder_ref.sim_topk(zp, zc, k)
+        paired = None
+        if targets is not None:
+            paired = (zp * zc[torch.from_numpy(np.asarray(targets)).long()]).sum(1)
+        return {"scores": s.contiguous(), "idx": i.to(torch.int32).contiguous(), "paired": paired, "embeds": None}
+
+
+def _small_setup():
+    from owc_b200 import arch as A
+    from owc_b200 import synth
+    from owc_b200.tokenizer import HostTokenizer
+    from owc_b200.weights import random_state_dict
+
+    arch = A.EncoderArch("tiny-bert", A.KIND_BERT, layers=1, hidden=256, heads=8, inter=512, vocab=2048, max_pos=64,
+                         type_vocab=2, ln_eps=1e-12)
+    vocab = synth.build_vocab("bert", arch.vocab)
+    words = synth.vocab_words(vocab)
+    classes = synth.make_class_names(12, words)
+    preds, targets = synth.make_predictions(61, classes, words)
+    return arch, random_state_dict(arch), HostTokenizer(vocab, "bert"), classes, preds, targets
+
+
+def _worker(rank, world, port, queue):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        arch, sd, tok, classes, preds, targets = _small_setup()
+        eng = _OracleEngine(arch, sd)
+        out = sharded.score_rows_sharded(eng, tok, classes, preds, targets, k=3)
+        if rank == 0:
+            queue.put({"scores": out["scores"], "idx": out["idx"], "paired": out["paired"], "calls": eng.encode_calls})
+        else:
+            assert out is None
+            queue.put({"calls": eng.encode_calls, "rank": rank})
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_sharded_scoring_world2_matches_single_process():
+    arch, sd, tok, classes, preds, targets = _small_setup()
+    single = sharded.score_rows_sharded(_OracleEngine(arch, sd), tok, classes, preds, targets, k=3)
+    assert single["scores"].shape == (61, 3)
+
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0 = next(r for r in results if "scores" in r)
+    r1 = next(r for r in results if "rank" in r)
+    assert np.array_equal(r0["idx"], single["idx"])
+    assert np.abs(r0["scores"] - single["scores"]).max() < 1e-6
+    assert np.abs(r0["paired"] - single["paired"]).max() < 1e-6
+    # rank 0 encodes the class names (1) + its rows (1); rank 1 only probes + encodes its rows: the
+    # class embeddings reach it by broadcast, not by re-encoding
+    assert r0["calls"] == 2 and r1["calls"] == 2
