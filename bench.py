@@ -87,23 +87,38 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def build_workload(rank: int, rows: int):
-    """Tokenised synthetic workload of one rank: Food101 names + distinct predictions."""
+WORKLOADS = {
+    # BASELINE.json configs[1] - the headline single-GPU configuration
+    "c2": {"arch": "minilm-l6", "classes": "food101", "desc": "c2: Food101 101 class names x 100k synthetic predictions per GPU, MiniLM-L6 arch, top-5 + paired score"},
+    # configs[2]: ImageNet-1k-scale matching with the mpnet-base architecture (parity-tested; bench on request)
+    "c3": {"arch": "mpnet-base", "classes": 1000, "desc": "c3: 1000 synthetic class names x synthetic predictions, mpnet-base arch, top-5 + paired score"},
+    # configs[3]: concept matching against a WordNet-noun-scale vocabulary
+    "c4": {"arch": "minilm-l6", "classes": 117_000, "desc": "c4: 117k synthetic names x synthetic predictions, MiniLM-L6 arch, fused top-5"},
+}
+
+
+def build_workload(rank: int, rows: int, workload: str = "c2"):
+    """Tokenised synthetic workload of one rank: class names + distinct predictions."""
     import numpy as np
 
     import owc_b200  # noqa: F401
+    from owc_b200 import arch as A
     from owc_b200 import synth
     from owc_b200.tokenizer import HostTokenizer
 
-    vocab = synth.build_vocab("bert")
+    spec = WORKLOADS[workload]
+    arch = A.ARCHS[spec["arch"]]
+    kind = "bert" if arch.kind == A.KIND_BERT else "mpnet"
+    vocab = synth.build_vocab(kind, arch.vocab)
     words = synth.vocab_words(vocab)
-    classes = synth.real_class_names("food101")
+    classes = (synth.real_class_names(spec["classes"]) if isinstance(spec["classes"], str)
+               else synth.make_class_names(spec["classes"], words, seed=1234))
     preds, targets = synth.make_predictions(rows, classes, words, seed=1234 + rank)
-    tok = HostTokenizer(vocab, "bert")
+    tok = HostTokenizer(vocab, kind)
     cids, ccu = tok.encode_packed(classes)
     pids, pcu = tok.encode_packed(preds)
     return {"vocab": vocab, "classes": classes, "preds": preds, "targets": np.asarray(targets, np.int32),
-            "cids": cids, "ccu": ccu, "pids": pids, "pcu": pcu, "tok": tok}
+            "cids": cids, "ccu": ccu, "pids": pids, "pcu": pcu, "tok": tok, "arch": arch, "desc": spec["desc"]}
 
 
 def cpu_reference_rate(sample_rows: int, steps: int, warmup: int, wl=None) -> dict:
@@ -121,7 +136,7 @@ def cpu_reference_rate(sample_rows: int, steps: int, warmup: int, wl=None) -> di
 
     torch.set_num_threads(os.cpu_count() or 1)
     wl = wl or build_workload(0, max(sample_rows, 1024))
-    arch = A.MINILM_L6
+    arch = wl["arch"]
     sd = random_state_dict(arch)
     hf_tok = build_hf_tokenizer(arch, wl["vocab"])
     classes = wl["classes"]
@@ -193,8 +208,8 @@ def run_ours(args) -> None:
         torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     rows = args.rows
-    wl = build_workload(rank, rows)
-    arch = A.MINILM_L6
+    wl = build_workload(rank, rows, args.workload)
+    arch = wl["arch"]
     eng = Engine(arch, random_state_dict(arch), device=local_rank, chunk_tokens=args.chunk_tokens)
     n_tok = int(wl["pcu"][-1])
     counts = [rows] * world
@@ -296,7 +311,7 @@ def run_ours(args) -> None:
         "metric": "predictions scored/sec (encode+match)", "value": value, "unit": "predictions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "c2: Food101 101 class names x 100k synthetic predictions per GPU, MiniLM-L6 arch, top-5 + paired score",
+        "config": {"workload": wl["desc"],
                    "rows_per_gpu": rows, "tokens_per_gpu": n_tok, "classes": len(wl["classes"]), "topk": TOPK,
                    "l2": "256 MB buffer written between timed steps; per-step activations (~GBs) also exceed the 126 MB L2",
                    "parallelism": f"rows sharded x{world}; class embeddings broadcast; results gathered on rank 0"},
@@ -332,6 +347,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="prediction rows per GPU")
     ap.add_argument("--chunk-tokens", type=int, default=0)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 is the headline; c3/c4 for the record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sim-leg", action="store_true")
     args = ap.parse_args()
