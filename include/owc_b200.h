@@ -167,6 +167,11 @@ int32_t owc_debug_gemm_loop(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, in
  * already resident in device memory (CUDA events on the ctx stream); ms_per_launch out.          */
 int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, int32_t k, int32_t iters,
                              float* ms_per_launch);
+/* Debug: timeline of the block-resident fused encoder kernel (enc_fused.cuh). When the ctx was created with
+ * OWC_FUSED_DBG=1 in the environment, the first SIMT thread of CTA 0 records clock64 at: block start,
+ * residual rows loaded, then per layer: attention block done, LayerNorm 1 done, feed-forward done,
+ * LayerNorm 2 done. Copies the 2048 int64 debug words (stamps, phase sums, event traces) of the most recent launch to `stamps` (HOST).      */
+int32_t owc_debug_fused_stamps(owc_encoder* enc, int64_t* stamps);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ EXPORTS = {
     "owc_debug_gemm_timeline": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32]),
     "owc_debug_gemm_loop": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_bench_sim_kernel": (_I32, [_P, _I64, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
+    "owc_debug_fused_stamps": (_I32, [_P, _P]),
 }
 
 _lib = None

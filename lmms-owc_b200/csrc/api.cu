@@ -15,6 +15,7 @@
 
 #include "../../include/owc_b200.h"
 #include "attn_mma.cuh"
+#include "enc_fused.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -70,6 +71,9 @@ struct owc_ctx {
   int fuse_ln = 1;         // fuse residual+LayerNorm into the O-proj / FFN2 epilogue (env OWC_FUSE_LN)
   int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
   int pdl = 1;             // programmatic dependent launch between the kernels of a layer (env OWC_PDL)
+  int fused = 1;           // block-resident fused encoder for MiniLM-width BERT, sequences <= 64 tokens (env OWC_FUSED)
+  int fused_waves = 4;     // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES)
+  int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -79,7 +83,7 @@ struct owc_ctx {
   std::vector<int> prof_cats;
   size_t prof_used = 0;
   // per-call scratch (grown on demand, reused across calls)
-  Buf ids, cu, targets, zp, zpb, zcb, zc32, cand_s, cand_i, out_s, out_i, out_p, tmp_a, tmp_b, tmp_c, tmp_d;
+  Buf ids, cu, targets, zp, zpb, zcb, zc32, cand_s, cand_i, out_s, out_i, out_p, tmp_a, tmp_b, tmp_c, tmp_d, blk;
 };
 
 struct LayerW {
@@ -104,6 +108,13 @@ struct owc_encoder {
   CUtensorMap tm_xb, tm_ao, tm_f;            // A-operand maps (box 128 rows x 64)
   CUtensorMap tmo_qkv, tmo_f, tmo_y;         // epilogue TMA-store maps (box 32 x 32)
   CUtensorMap tmo_x, tmo_xb;                 // fused-LN epilogue: residual stream (fp32, load + store) and its bf16 copy
+  // block-resident fused encoder (enc_fused.cuh): layer-stacked bf16 weights, QKV rows regrouped per head
+  bool fused_ok = false;
+  __nv_bfloat16 *fw_qkv = nullptr, *fw_o = nullptr, *fw_1 = nullptr, *fw_2 = nullptr;
+  CUtensorMap tmf_qkv, tmf_o, tmf_1, tmf_2;
+  int fcap = 0;                    // tokens per fused launch
+  float* fx = nullptr;             // [fcap + 128, H] fp32 residual stream of a fused chunk
+  long long* fdbg = nullptr;       // [1024] timeline stamps + event traces
 };
 
 constexpr int kEncBN = 192;   // divides 3H, H and I of both architectures (1152/384/1536, 2304/768/3072)
@@ -356,6 +367,9 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* fl = getenv("OWC_FUSE_LN")) c->fuse_ln = atoi(fl) != 0;
   if (const char* ar = getenv("OWC_ARES")) c->ares = atoi(ar) != 0;
   if (const char* pd = getenv("OWC_PDL")) c->pdl = atoi(pd) != 0;
+  if (const char* fu = getenv("OWC_FUSED")) c->fused = atoi(fu) != 0;
+  if (const char* fw = getenv("OWC_FUSED_WAVES")) c->fused_waves = std::max(1, std::min(64, atoi(fw)));
+  if (const char* fd = getenv("OWC_FUSED_DBG")) c->fused_dbg = atoi(fd) != 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -382,7 +396,7 @@ extern "C" int32_t owc_ctx_destroy(owc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   Buf* bufs[] = {&c->ids, &c->cu, &c->targets, &c->zp, &c->zpb, &c->zcb, &c->zc32, &c->cand_s, &c->cand_i,
-                 &c->out_s, &c->out_i, &c->out_p, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d};
+                 &c->out_s, &c->out_i, &c->out_p, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->blk};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_status) cudaFree(c->d_status);
@@ -445,6 +459,19 @@ extern "C" int32_t owc_ctx_profile_end(owc_ctx* c, owc_profile* out) {
 // ------------------------------------------------------------------------------------------------
 // ABI: encoder load / destroy
 // ------------------------------------------------------------------------------------------------
+// Wqkv [3H, H] (rows q | k | v, each head-major) -> rows grouped per head: [head][q 32 | k 32 | v 32][H],
+// so one 96-row tile of the fused encoder is one head's q|k|v projection (H = 384, 12 heads of 32).
+__global__ void __launch_bounds__(256) k_regroup_qkv(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
+  constexpr int H = fz::H, D = fz::D;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte piece (8 bf16) of a destination row
+  if (i >= 3 * H * H / 8) return;
+  const int drow = i / (H / 8), piece = i % (H / 8);
+  const int head = drow / (3 * D), p = (drow / D) % 3, d = drow % D;
+  const int srow = p * H + head * D + d;
+  reinterpret_cast<uint4*>(dst)[static_cast<size_t>(drow) * (H / 8) + piece] =
+      reinterpret_cast<const uint4*>(src)[static_cast<size_t>(srow) * (H / 8) + piece];
+}
+
 static size_t blob_floats(const owc_arch& a) {
   const size_t h = a.hidden, i = a.inter;
   size_t n = (size_t)a.vocab * h + (size_t)a.max_pos * h + (size_t)a.type_vocab * h + 2 * h;
@@ -457,7 +484,8 @@ extern "C" int32_t owc_encoder_destroy(owc_encoder* e) {
   if (!e) return 0;
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
-  void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32};
+  void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32,
+                  e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -548,6 +576,32 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   if (make_out_tmap(c, &e->tmo_qkv, e->qkv, cap, 3 * h, true) || make_out_tmap(c, &e->tmo_f, e->f, cap, I, true) ||
       make_out_tmap(c, &e->tmo_y, e->y, cap, h, false) || make_out_tmap(c, &e->tmo_x, e->x, cap, h, false) ||
       make_out_tmap(c, &e->tmo_xb, e->xb, cap, h, true)) { owc_encoder_destroy(e); return 1; }
+  // ---- block-resident fused encoder: MiniLM-width BERT only (enc_fused.cuh) ----
+  e->fused_ok = a.kind == OWC_ARCH_BERT && a.hidden == fz::H && a.heads == fz::HEADS && a.inter % 128 == 0 && a.inter >= 128;
+  if (e->fused_ok) {
+    const size_t L = a.layers;
+    LOAD_CU(cudaMalloc(&e->fw_qkv, L * 3 * h * h * 2));
+    LOAD_CU(cudaMalloc(&e->fw_o, L * h * h * 2));
+    LOAD_CU(cudaMalloc(&e->fw_1, L * I * h * 2));
+    LOAD_CU(cudaMalloc(&e->fw_2, L * h * I * 2));
+    for (size_t l = 0; l < L; ++l) {
+      const LayerW& Lw = e->layers[l];
+      k_regroup_qkv<<<static_cast<unsigned>((3 * h * h / 8 + 255) / 256), 256, 0, c->stream>>>(Lw.wqkv, e->fw_qkv + l * 3 * h * h);
+      if (check_launch(c, "k_regroup_qkv")) { owc_encoder_destroy(e); return 1; }
+      LOAD_CU(cudaMemcpyAsync(e->fw_o + l * h * h, Lw.wo, h * h * 2, cudaMemcpyDeviceToDevice, c->stream));
+      LOAD_CU(cudaMemcpyAsync(e->fw_1 + l * I * h, Lw.w1, I * h * 2, cudaMemcpyDeviceToDevice, c->stream));
+      LOAD_CU(cudaMemcpyAsync(e->fw_2 + l * h * I, Lw.w2, h * I * 2, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (make_tmap(c, &e->tmf_qkv, e->fw_qkv, L * 3 * h, h, 48) || make_tmap(c, &e->tmf_o, e->fw_o, L * h, h, 64) ||
+        make_tmap(c, &e->tmf_1, e->fw_1, L * I, h, 64) || make_tmap(c, &e->tmf_2, e->fw_2, L * h, I, 64)) { owc_encoder_destroy(e); return 1; }
+    e->fcap = (c->sm_count / 2) * 256 * c->fused_waves;
+    LOAD_CU(cudaMalloc(&e->fx, (static_cast<size_t>(e->fcap) + 128) * h * sizeof(float)));
+    LOAD_CU(cudaMemsetAsync(e->fx, 0, (static_cast<size_t>(e->fcap) + 128) * h * sizeof(float), c->stream));
+    LOAD_CU(cudaMalloc(&e->fdbg, 2048 * sizeof(long long)));
+    LOAD_CU(cudaMemsetAsync(e->fdbg, 0, 2048 * sizeof(long long), c->stream));
+    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
+    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
+  }
   LOAD_CU(cudaStreamSynchronize(c->stream));  // `weights` may be freed by the caller after return
 #undef LOAD_CU
 #undef LOAD_FAIL
@@ -741,6 +795,90 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
   return 0;
 }
 
+// Block-resident fused path (enc_fused.cuh): sequences are grouped greedily into 128-token row blocks of
+// whole sequences; each launch carries up to e->fcap tokens worth of blocks through every layer.
+// Per launch: k_embed_ln -> fx (fp32), k_encoder_fused (fx in place), k_pool_l2.
+static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* cu, int n_seq, float* z,
+                            __nv_bfloat16* zb) {
+  owc_ctx* c = e->ctx;
+  const owc_arch& a = e->arch;
+  const int H = a.hidden;
+  // ---- row blocks over the whole call ----
+  std::vector<int32_t> blk;
+  blk.reserve(static_cast<size_t>(cu[n_seq]) / 96 + 2);
+  blk.push_back(0);
+  int rows = 0, cnt = 0;
+  for (int s = 0; s < n_seq; ++s) {
+    const int len = cu[s + 1] - cu[s];
+    if (rows + len > 128 || cnt == 128) {
+      blk.push_back(s);
+      rows = 0;
+      cnt = 0;
+    }
+    rows += len;
+    ++cnt;
+  }
+  blk.push_back(n_seq);
+  const int n_blk = static_cast<int>(blk.size()) - 1;
+  const void* d_blk = nullptr;
+  OWC_TRY(to_device(c, c->blk, blk.data(), blk.size() * sizeof(int32_t), OWC_MEM_HOST, &d_blk));
+
+  FusedArgs fa{};
+  fa.x = e->fx;
+  fa.cu = d_cu;
+  fa.layers = a.layers;
+  fa.n_chunks = a.inter / 128;
+  const LayerW& L0 = e->layers[0];
+  fa.layer_stride = a.layers > 1 ? static_cast<long long>(e->layers[1].bqkv - L0.bqkv) : 0;
+  fa.bqkv = L0.bqkv; fa.bo = L0.bo; fa.ln1g = L0.ln1g; fa.ln1b = L0.ln1b;
+  fa.b1 = L0.b1; fa.b2 = L0.b2; fa.ln2g = L0.ln2g; fa.ln2b = L0.ln2b;
+  fa.ln_eps = a.ln_eps;
+  fa.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(H / a.heads));
+  fa.dbg = c->fused_dbg ? e->fdbg : nullptr;
+  if (const char* ab = getenv("OWC_FUSED_ABLATE")) fa.ablate = atoi(ab);   // debug only: results are wrong when set
+
+  int b0 = 0;
+  while (b0 < n_blk) {
+    int b1 = b0 + 1;
+    while (b1 < n_blk && cu[blk[b1 + 1]] - cu[blk[b0]] <= e->fcap) ++b1;
+    const int seq0 = blk[b0], nseq = blk[b1] - blk[b0];
+    const int tok0 = cu[seq0], M = cu[blk[b1]] - tok0;
+    if (M > 0) {
+      EmbedArgs ea{};
+      ea.ids = d_ids; ea.cu = d_cu; ea.seq0 = seq0; ea.n_seq = nseq; ea.tok0 = tok0;
+      ea.word = e->word; ea.pos = e->pos; ea.type0 = e->type0; ea.gamma = e->emb_g; ea.beta = e->emb_b;
+      ea.eps = a.ln_eps; ea.H = H; ea.vocab = a.vocab; ea.max_pos = a.max_pos;
+      ea.mpnet = 0; ea.pad_id = a.pad_id;
+      ea.x = e->fx; ea.xb = nullptr; ea.status = c->d_status;
+      {
+        ProfScope prof(c, OWC_KCAT_EMBED);
+        k_embed_ln<3><<<(nseq + 3) / 4, 128, 0, c->stream>>>(ea);
+      }
+      OWC_TRY(check_launch(c, "k_embed_ln"));
+      fa.blk_seq = static_cast<const int32_t*>(d_blk) + b0;
+      fa.n_blk = b1 - b0;
+      fa.tok0 = tok0;
+      const int pairs = (fa.n_blk + 1) / 2;
+      const int clusters = std::max(1, std::min(pairs, c->sm_count / 2));
+      {
+        ProfScope prof(c, OWC_KCAT_GEMM);
+        if (c->fused_dbg) k_encoder_fused<true><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
+        else k_encoder_fused<false><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
+      }
+      OWC_TRY(check_launch(c, "k_encoder_fused"));
+    }
+    {
+      ProfScope prof(c, OWC_KCAT_POOL);
+      k_pool_l2<3><<<(nseq + 3) / 4, 128, 0, c->stream>>>(e->fx, d_cu, seq0, nseq, tok0, H, z, zb);
+    }
+    OWC_TRY(check_launch(c, "k_pool_l2"));
+    c->stats.tokens_encoded += M;
+    c->stats.sequences_encoded += nseq;
+    b0 = b1;
+  }
+  return 0;
+}
+
 // Validates cu_seqlens, stages ids/cu on the device and runs every chunk. z: device fp32 [n_seq,H];
 // zb: device bf16 [n_seq,H] or nullptr.
 static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const int32_t* cu, int n_seq, int precision,
@@ -751,8 +889,10 @@ static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const i
   if (n_seq == 0) return 0;
   if (cu[0] != 0) return fail("cu_seqlens[0] must be 0");
   const int max_len = e->arch.kind == OWC_ARCH_MPNET ? e->arch.max_pos - 2 : e->arch.max_pos;
+  int longest = 0;
   for (int s = 0; s < n_seq; ++s) {
     const int len = cu[s + 1] - cu[s];
+    longest = std::max(longest, len);
     if (len < 0) return fail("cu_seqlens decreases at %d", s);
     if (len > max_len) return fail("sequence %d has %d tokens; the position table allows %d (truncate on the host)", s, len, max_len);
   }
@@ -762,6 +902,8 @@ static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const i
   const void* d_cu = nullptr;
   OWC_TRY(to_device(c, c->ids, ids, static_cast<size_t>(std::max<long long>(total, 1)) * sizeof(int32_t), ids_space, &d_ids));
   OWC_TRY(to_device(c, c->cu, cu, (static_cast<size_t>(n_seq) + 1) * sizeof(int32_t), OWC_MEM_HOST, &d_cu));
+  if (precision == OWC_PREC_BF16 && c->fused && e->fused_ok && longest <= 64)
+    return encode_all_fused(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), cu, n_seq, z, zb);
   int s0 = 0;
   while (s0 < n_seq) {
     int s1 = s0, max_t = 1;
@@ -1120,6 +1262,15 @@ extern "C" int32_t owc_debug_gemm_loop(owc_ctx* c, int32_t m, int32_t n, int32_t
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_per_launch = ms / iters;
+  return 0;
+}
+
+extern "C" int32_t owc_debug_fused_stamps(owc_encoder* e, int64_t* out64) {
+  if (!e || !out64) return fail("owc_debug_fused_stamps: NULL argument");
+  if (!e->fdbg) return fail("fused encoder not available for this architecture");
+  CU_OK(cudaSetDevice(e->ctx->device));
+  CU_OK(cudaMemcpyAsync(out64, e->fdbg, 2048 * sizeof(long long), cudaMemcpyDeviceToHost, e->ctx->stream));
+  CU_OK(cudaStreamSynchronize(e->ctx->stream));
   return 0;
 }
 
