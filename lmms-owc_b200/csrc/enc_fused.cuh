@@ -68,7 +68,7 @@ constexpr int OFF_QKV = OFF_U + 32768;      // 128 x 208 = 26624
 constexpr int OFF_FC = OFF_U;               // 2 x 32768
 constexpr int OFF_RING = OFF_U + 65536;     // 163840
 constexpr int OFF_TAIL = OFF_RING + SLOTS * SLOT;   // 221184
-constexpr int TAIL_BYTES = 5120;
+constexpr int TAIL_BYTES = 1024 + 4096 + 3 * 384 * 4;   // barriers / tables, LayerNorm statistics, LayerNorm bias|gamma|beta
 constexpr int SMEM_BYTES = OFF_TAIL + TAIL_BYTES + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t TM_X = 0, TM_T1 = 384;   // TMEM column offsets
@@ -258,16 +258,23 @@ __device__ __forceinline__ void attn_head_smem(const __nv_bfloat16* qkv, uint8_t
         }
       }
     }
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    float inv0, inv1;   // sums are >= 1 (the row maximum contributes 2^0): the approximate reciprocal is exact enough
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(sum0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(sum1));
     const int gr0 = beg + r0, gr1 = beg + r1;
+    if (r0 < T) {
+      uint8_t* p0 = ao_tile + gr0 * 128 + t4 * 4;
+      const int sw0 = gr0 & 7;
 #pragma unroll
-    for (int dn = 0; dn < DN; ++dn) {
-      if (r0 < T)
-        *reinterpret_cast<uint32_t*>(ao_tile + gr0 * 128 + (((cb + dn) ^ (gr0 & 7)) << 4) + t4 * 4) =
-            pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-      if (r1 < T)
-        *reinterpret_cast<uint32_t*>(ao_tile + gr1 * 128 + (((cb + dn) ^ (gr1 & 7)) << 4) + t4 * 4) =
-            pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+      for (int dn = 0; dn < DN; ++dn)
+        *reinterpret_cast<uint32_t*>(p0 + (((cb + dn) ^ sw0) << 4)) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+    }
+    if (r1 < T) {
+      uint8_t* p1 = ao_tile + gr1 * 128 + t4 * 4;
+      const int sw1 = gr1 & 7;
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn)
+        *reinterpret_cast<uint32_t*>(p1 + (((cb + dn) ^ sw1) << 4)) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
     }
   }
 }
@@ -316,6 +323,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256);
   int* seq_row = reinterpret_cast<int*>(tail + 320);    // [<= 130] first row of each sequence of this CTA's block
   float* stat_s = reinterpret_cast<float*>(tail + 1024);   // [NSIMT][32][2]
+  float* lnp = reinterpret_cast<float*>(tail + 1024 + 4096);   // [3][384]: bias | gamma | beta of the next LayerNorm
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -540,14 +548,28 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (lane == 0) arrive_leader(xb_ready);
     };
     // LayerNorm of (x + bias) over the row, in place; optionally stores the fp32 row to global (last layer)
-    auto layer_norm = [&](const float* bias, const float* gamma, const float* beta, bool to_global, float* gout) {
+    // LayerNorm of (x + bias) over the row, in place (x in TMEM + XB); the block's last one writes the fp32 row
+    // to global instead. Two passes over TMEM (statistics, then normalise) in packed fp32x2 arithmetic; the
+    // NW warps of a lane quadrant each own every NW-th 32-column chunk and exchange partial statistics.
+    // Shared memory left to the L1 by this kernel is ~0, so every __ldg is an L2 round trip: the parameters of the
+    // next LayerNorm are staged in shared memory at the start of the phase that ends with it.
+    auto stage_ln_params = [&](const float* bias, const float* gamma, const float* beta) {
+      named_bar_sync(1, NSIMT * 32);   // the previous LayerNorm's readers are done
+      const int i = threadIdx.x;
+      if (i < 3 * (H / 4)) {
+        const float* src = (i < H / 4) ? bias : (i < 2 * (H / 4) ? gamma : beta);
+        reinterpret_cast<float4*>(lnp)[i] = __ldg(reinterpret_cast<const float4*>(src) + (i % (H / 4)));
+      }
+    };
+    auto layer_norm = [&](bool to_global, float* gout) {
       pa.mark(15);
       mbar_wait(accx_full, n_accx & 1); ++n_accx;
       pa.mark(6);
       pa.event(20);   // accx_full observed
       tc_fence_after();
       if (a.ablate & 4) return;
-      float sum = 0.f, sq = 0.f;
+      named_bar_sync(1, NSIMT * 32);   // the staged parameters (stage_ln_params) are visible to every warp
+      uint64_t s2 = 0ull, q2 = 0ull;   // (0.f, 0.f)
       uint32_t v[32];
 #pragma unroll 1
       for (int k = part; k < H / 32; k += NW) {
@@ -555,29 +577,34 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld_wait_dep(v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + k * 32) + j);
-          const float x0 = __uint_as_float(v[4 * j + 0]) + b.x;
-          const float x1 = __uint_as_float(v[4 * j + 1]) + b.y;
-          const float x2 = __uint_as_float(v[4 * j + 2]) + b.z;
-          const float x3 = __uint_as_float(v[4 * j + 3]) + b.w;
-          sum += (x0 + x1) + (x2 + x3);
-          sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+          const float4 b = *reinterpret_cast<const float4*>(lnp + k * 32 + 4 * j);
+          const uint64_t u0 = f2_add(f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), f2_pack(b.x, b.y));
+          const uint64_t u1 = f2_add(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), f2_pack(b.z, b.w));
+          s2 = f2_add(s2, f2_add(u0, u1));
+          q2 = f2_fma(u0, u0, q2);
+          q2 = f2_fma(u1, u1, q2);
         }
       }
       pa.mark(7);
-      stat_s[(warp_e * 32 + lane) * 2 + 0] = sum;
-      stat_s[(warp_e * 32 + lane) * 2 + 1] = sq;
+      float sum, sq, t0, t1;
+      f2_unpack(s2, t0, t1); sum = t0 + t1;
+      f2_unpack(q2, t0, t1); sq = t0 + t1;
+      float* st = stat_s;
+      st[(warp_e * 32 + lane) * 2 + 0] = sum;
+      st[(warp_e * 32 + lane) * 2 + 1] = sq;
       named_bar_sync(2 + q, NW * 32);
       pa.mark(8);
       sum = 0.f; sq = 0.f;
 #pragma unroll
       for (int p = 0; p < NW; ++p) {
-        sum += stat_s[((p * 4 + (warp_e & 3)) * 32 + lane) * 2 + 0];
-        sq += stat_s[((p * 4 + (warp_e & 3)) * 32 + lane) * 2 + 1];
+        const float2 t = *reinterpret_cast<const float2*>(st + ((p * 4 + (warp_e & 3)) * 32 + lane) * 2);
+        sum += t.x;
+        sq += t.y;
       }
       const float mean = sum * (1.0f / H);
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / H) - mean * mean, 0.f) + a.ln_eps);
-      const float nmr = -mean * rstd;
+      const uint64_t rstd2 = f2_pack(rstd, rstd);
+      const uint64_t nmr2 = f2_pack(-mean * rstd, -mean * rstd);
 #pragma unroll 1
       for (int k = part; k < H / 32; k += NW) {
         tmem_ld_32x32(tq + TM_X + static_cast<uint32_t>(k * 32), v);
@@ -585,13 +612,15 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + k * 32) + j);
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + k * 32) + j);
-          const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + k * 32) + j);
-          f[4 * j + 0] = fmaf(fmaf(__uint_as_float(v[4 * j + 0]) + b.x, rstd, nmr), gm.x, bt.x);
-          f[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]) + b.y, rstd, nmr), gm.y, bt.y);
-          f[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]) + b.z, rstd, nmr), gm.z, bt.z);
-          f[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]) + b.w, rstd, nmr), gm.w, bt.w);
+          const float4 b = *reinterpret_cast<const float4*>(lnp + k * 32 + 4 * j);
+          const float4 gm = *reinterpret_cast<const float4*>(lnp + H + k * 32 + 4 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(lnp + 2 * H + k * 32 + 4 * j);
+          uint64_t u0 = f2_add(f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), f2_pack(b.x, b.y));
+          uint64_t u1 = f2_add(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), f2_pack(b.z, b.w));
+          u0 = f2_fma(f2_fma(u0, rstd2, nmr2), f2_pack(gm.x, gm.y), f2_pack(bt.x, bt.y));
+          u1 = f2_fma(f2_fma(u1, rstd2, nmr2), f2_pack(gm.z, gm.w), f2_pack(bt.z, bt.w));
+          f2_unpack(u0, f[4 * j + 0], f[4 * j + 1]);
+          f2_unpack(u1, f[4 * j + 2], f[4 * j + 3]);
         }
         if (to_global) {   // warp-uniform: the block's last LayerNorm leaves the chip
           if (gout != nullptr) {
@@ -652,15 +681,24 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if constexpr (DBG) pa.tracing = (bp == cluster_id && l == 1);
         const size_t lo = static_cast<size_t>(l) * static_cast<size_t>(a.layer_stride);
         // =========== attention block ===========
+        stage_ln_params(a.bo + lo, a.ln1g + lo, a.ln1b + lo);
         const float* bqkv = a.bqkv + lo;
         for (int h = 0; h < HEADS; ++h) {
           // ---- drain T1 = [q|k|v] of head h: + bias -> bf16 rows in QKV ----
+          constexpr int CP = 96 / NW;   // columns per warp
+          float4 bq[CP / 4];            // this warp's bias slice, fetched while the MMAs of the tile still run
+#pragma unroll
+          for (int i = 0; i < CP / 8; ++i) {
+            const int col = part * CP + i * 8;                        // 8 columns never straddle q|k|v
+            const float* bp8 = bqkv + (col >> 5) * H + h * D + (col & 31);
+            bq[2 * i] = __ldg(reinterpret_cast<const float4*>(bp8));
+            bq[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(bp8) + 1);
+          }
           pa.mark(15);
           mbar_wait(t1_full, n_t1 & 1); ++n_t1;
           pa.mark(0);
           pa.event(0);   // t1_full observed (attention)
           tc_fence_after();
-          constexpr int CP = 96 / NW;   // columns per warp
           uint32_t v[CP];
           if (!(a.ablate & 8)) {
             tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(part * CP), v);
@@ -678,10 +716,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             uint8_t* dst = reinterpret_cast<uint8_t*>(QKV) + r * (QP * 2) + part * CP * 2;
 #pragma unroll
             for (int i = 0; i < CP / 8; ++i) {
-              const int col = part * CP + i * 8;                        // 8 columns never straddle q|k|v
-              const float* bp8 = bqkv + (col >> 5) * H + h * D + (col & 31);
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp8) + 1);
+              const float4 b0 = bq[2 * i], b1 = bq[2 * i + 1];
               uint4 w;
               w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x, __uint_as_float(v[8 * i + 1]) + b0.y);
               w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + b0.z, __uint_as_float(v[8 * i + 3]) + b0.w);
@@ -720,18 +755,22 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           pa.event(4);   // head done (after barrier)
         }
         FZ_STAMP();
-        layer_norm(a.bo + lo, a.ln1g + lo, a.ln1b + lo, false, nullptr);
+        layer_norm(false, nullptr);
         publish_x();
         FZ_STAMP();
         // =========== feed-forward block ===========
+        stage_ln_params(a.b2 + lo, a.ln2g + lo, a.ln2b + lo);
         const float* b1p = a.b1 + lo;
         for (int c = 0; c < a.n_chunks; ++c) {
+          constexpr int CP = 128 / NW;   // columns per warp
+          float4 bf1[CP / 4];            // bias slice, fetched while the MMAs of the tile still run
+#pragma unroll
+          for (int i = 0; i < CP / 4; ++i) bf1[i] = __ldg(reinterpret_cast<const float4*>(b1p + c * 128 + part * CP) + i);
           pa.mark(15);
           mbar_wait(t1_full, n_t1 & 1); ++n_t1;
           pa.mark(10);
           pa.event(10);   // t1_full observed (FFN)
           tc_fence_after();
-          constexpr int CP = 128 / NW;   // columns per warp (64 = one k-block of the FFN2 A operand)
           uint32_t v[CP];
           if (!(a.ablate & 8)) {
             tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(part * CP), v);
@@ -746,11 +785,10 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           pa.mark(11);
           pa.event(11);   // drained
           const int fb = c & 1;
-          const float* bc = b1p + c * 128 + part * CP;
           if (!(a.ablate & 2)) {
 #pragma unroll
           for (int i = 0; i < CP / 4; ++i) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bc) + i);
+            const float4 b = bf1[i];
             float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
             float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
             gelu_fast2(x0, x1);
@@ -783,7 +821,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         FZ_STAMP();
         const bool last = l + 1 == a.layers;
         float* gout = (last && r < ntok) ? a.x + static_cast<size_t>(row0 + r) * H : nullptr;
-        layer_norm(a.b2 + lo, a.ln2g + lo, a.ln2b + lo, last, gout);   // rows past ntok write nowhere
+        layer_norm(last, gout);   // rows past ntok write nowhere
         if (!last) publish_x();
         FZ_STAMP();
       }

@@ -1,0 +1,144 @@
+"""GPU parity of the block-resident fused encoder kernel (csrc/enc_fused.cuh) through the C-ABI: against the
+per-GEMM kernel path of the same library, against the oracle, and on the edge cases of its row-block packing
+(pytest -m gpu). The fused kernel serves MiniLM-width BERT encoders in bf16 mode when no sequence exceeds 64
+tokens; everything else takes the per-GEMM path, which these tests use as the second opinion."""
+
+import numpy as np
+import pytest
+
+import owc_b200  # noqa: F401
+from oracle import encoder_ref
+from owc_b200 import synth
+from owc_b200.engine import Engine
+from owc_b200.tokenizer import HostTokenizer
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(b, monkeypatch, fused: int, waves: int | None = None):
+    monkeypatch.setenv("OWC_FUSED", str(fused))
+    if waves is not None:
+        monkeypatch.setenv("OWC_FUSED_WAVES", str(waves))
+    else:
+        monkeypatch.delenv("OWC_FUSED_WAVES", raising=False)
+    return Engine(b.arch, b.sd, device=0)
+
+
+@pytest.fixture()
+def engines(minilm, monkeypatch):
+    fused = _engine(minilm, monkeypatch, 1)
+    plain = _engine(minilm, monkeypatch, 0)
+    yield fused, plain
+    fused.close()
+    plain.close()
+
+
+def _ragged_texts(words, n, seed, lo=1, hi=24):
+    rng = np.random.default_rng(seed)
+    return [" ".join(rng.choice(words, size=int(k))) for k in rng.integers(lo, hi, size=n)]
+
+
+def _launches(eng, fn):
+    a = eng.stats()["kernel_launches"]
+    out = fn()
+    return out, eng.stats()["kernel_launches"] - a
+
+
+def test_fused_path_is_taken_and_matches_per_gemm_path(minilm, engines):
+    fused, plain = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    texts = _ragged_texts(minilm.words, 3000, 1)
+    ids, cu = tok.encode_packed(texts)
+    assert np.diff(cu).max() <= 64
+    zf, nf = _launches(fused, lambda: fused.encode(ids, cu))
+    zp, np_ = _launches(plain, lambda: plain.encode(ids, cu))
+    # one embed + one fused + one pool launch per chunk, against ~27 launches per chunk on the per-GEMM path
+    assert nf < np_ / 3, (nf, np_)
+    assert np.abs(zf - zp).max() < 1e-3
+    assert np.abs(np.linalg.norm(zf, axis=1) - 1).max() < 1e-5
+    want = encoder_ref.encode_strings(minilm.sd, minilm.arch, minilm.hf_tok, texts[:400]).numpy()
+    assert np.abs(zf[:400] - want).max() < 1e-3   # north star: 1e-2 on the cosine in bf16 mode
+
+
+def test_fused_matches_reference_golden(minilm, engines):
+    fused, _ = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    for col, gold in (("class_names", "class_embeds"), ("preds", "pred_embeds")):
+        ids, cu = tok.encode_packed([str(s) for s in minilm.gold[col]])
+        assert np.diff(cu).max() <= 64
+        z = fused.encode(ids, cu)
+        assert np.abs(z - minilm.gold[gold]).max() < 1e-3
+
+
+@pytest.mark.parametrize("lens", [
+    [1], [64], [64, 64], [64, 64, 1], [63, 2, 63, 2], [3] * 43, [2] * 200, [1] * 300,
+    [64] * 5 + [1] * 7 + [33] * 9, [5, 0, 7, 0, 0, 64, 0], [0, 0, 3], [128 // 3] * 3 + [2],
+])
+def test_row_block_packing_edges(minilm, engines, lens):
+    """Sequences exactly filling a 128-row block, blocks closed by the 128-sequence cap, empty sequences, a single
+    row, odd block counts (the pair's second CTA has no block)."""
+    fused, plain = engines
+    rng = np.random.default_rng(len(lens) * 1000 + sum(lens))
+    ids = rng.integers(5, minilm.arch.vocab, size=sum(lens)).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    zf = fused.encode(ids, cu)
+    zp = plain.encode(ids, cu)
+    empty = np.asarray(lens) == 0
+    assert np.isnan(zf[empty]).all() and np.isnan(zp[empty]).all()       # _text.py:202: no epsilon
+    assert np.isfinite(zf[~empty]).all()
+    assert np.abs(zf[~empty] - zp[~empty]).max() < 1e-3
+
+
+def test_position_in_block_and_launch_size_are_invisible(minilm, monkeypatch):
+    """A sequence's embedding does not depend on its neighbours, its row inside the block, or how many block
+    pairs one launch carries."""
+    tok = HostTokenizer(minilm.vocab, "bert")
+    texts = _ragged_texts(minilm.words, 5000, 3)
+    ids, cu = tok.encode_packed(texts)
+    e4 = _engine(minilm, monkeypatch, 1)
+    e1 = _engine(minilm, monkeypatch, 1, waves=1)
+    try:
+        z4 = e4.encode(ids, cu)
+        z1, n1 = _launches(e1, lambda: e1.encode(ids, cu))
+        assert n1 > 3          # several launches at one wave per launch
+        assert np.array_equal(z1, z4)
+        perm = np.random.default_rng(0).permutation(len(texts))
+        ids2, cu2 = tok.encode_packed([texts[i] for i in perm])
+        z2 = e4.encode(ids2, cu2)
+        assert np.abs(z2 - z4[perm]).max() < 1e-6
+        ids3, cu3 = tok.encode_packed([texts[17]])
+        assert np.abs(e4.encode(ids3, cu3)[0] - z4[17]).max() < 1e-6
+    finally:
+        e4.close()
+        e1.close()
+
+
+def test_longer_sequences_fall_back_to_the_per_gemm_path(minilm, engines):
+    fused, plain = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    texts = _ragged_texts(minilm.words, 200, 5) + [" ".join(minilm.words[:90])]
+    ids, cu = tok.encode_packed(texts)
+    assert np.diff(cu).max() > 64
+    zf = fused.encode(ids, cu)
+    zp = plain.encode(ids, cu)
+    assert np.array_equal(zf, zp)
+
+
+def test_score_through_fused_encoder(minilm, engines):
+    fused, plain = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    cls = synth.real_class_names("food101")
+    preds, targets = synth.make_predictions(4000, cls, minilm.words, seed=11)
+    cids, ccu = tok.encode_packed(cls)
+    pids, pcu = tok.encode_packed(preds)
+    t = np.asarray(targets, np.int32)
+    out = []
+    for e in (fused, plain):
+        zc = e.encode(cids, ccu, out="device")
+        out.append(e.score(pids, pcu, zc, targets=t, k=5))
+    f, p = out
+    assert np.abs(f["paired"] - p["paired"]).max() < 1e-3
+    assert np.abs(f["scores"] - p["scores"]).max() < 1e-3
+    margin = p["scores"][:, 0] - p["scores"][:, 1]
+    clear = margin >= 1e-3
+    assert (f["idx"][clear, 0] == p["idx"][clear, 0]).all()
