@@ -72,7 +72,7 @@ struct owc_ctx {
   int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
   int pdl = 1;             // programmatic dependent launch between the kernels of a layer (env OWC_PDL)
   int fused = 1;           // block-resident fused encoder for MiniLM-width BERT, sequences <= 64 tokens (env OWC_FUSED)
-  int fused_waves = 4;     // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES)
+  int fused_waves = 8;     // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES)
   int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
@@ -592,9 +592,9 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
       LOAD_CU(cudaMemcpyAsync(e->fw_1 + l * I * h, Lw.w1, I * h * 2, cudaMemcpyDeviceToDevice, c->stream));
       LOAD_CU(cudaMemcpyAsync(e->fw_2 + l * h * I, Lw.w2, h * I * 2, cudaMemcpyDeviceToDevice, c->stream));
     }
-    if (make_tmap(c, &e->tmf_qkv, e->fw_qkv, L * 3 * h, h, 48) || make_tmap(c, &e->tmf_o, e->fw_o, L * h, h, 64) ||
-        make_tmap(c, &e->tmf_1, e->fw_1, L * I, h, 64) || make_tmap(c, &e->tmf_2, e->fw_2, L * h, I, 64)) { owc_encoder_destroy(e); return 1; }
-    e->fcap = (c->sm_count / 2) * 256 * c->fused_waves;
+    if (make_tmap(c, &e->tmf_qkv, e->fw_qkv, L * 3 * h, h, 48) || make_tmap(c, &e->tmf_o, e->fw_o, L * h, h, 96) ||
+        make_tmap(c, &e->tmf_1, e->fw_1, L * I, h, 64) || make_tmap(c, &e->tmf_2, e->fw_2, L * h, I, 96)) { owc_encoder_destroy(e); return 1; }
+    e->fcap = (c->sm_count / 2) * 256 * c->fused_waves;   // rows of (SM pairs x waves) block pairs
     LOAD_CU(cudaMalloc(&e->fx, (static_cast<size_t>(e->fcap) + 128) * h * sizeof(float)));
     LOAD_CU(cudaMemsetAsync(e->fx, 0, (static_cast<size_t>(e->fcap) + 128) * h * sizeof(float), c->stream));
     LOAD_CU(cudaMalloc(&e->fdbg, 2048 * sizeof(long long)));
@@ -839,8 +839,8 @@ static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t*
 
   int b0 = 0;
   while (b0 < n_blk) {
-    int b1 = b0 + 1;
-    while (b1 < n_blk && cu[blk[b1 + 1]] - cu[blk[b0]] <= e->fcap) ++b1;
+    // whole waves: every cluster gets the same number of block pairs (a launch ends when its slowest cluster does)
+    const int b1 = std::min(n_blk, b0 + e->fcap / 128);
     const int seq0 = blk[b0], nseq = blk[b1] - blk[b0];
     const int tok0 = cu[seq0], M = cu[blk[b1]] - tok0;
     if (M > 0) {

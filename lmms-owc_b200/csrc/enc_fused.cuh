@@ -15,7 +15,8 @@
 //         QKV 26 KB        current head's q|k|v rows (bf16, 208 B pitch) for the mma.sync attention
 //         AO  2 x 16 KB    attention output of a head PAIR as A operand (K = 64) of the O-projection
 //         FC  2 x 32 KB    GELU(FFN1 slice) as A operand (K = 128) of FFN2 (aliases QKV/AO)
-//         RING 7 x 8 KB    weight tiles (64 or 48 rows x 64 K) streamed by TMA
+//         RING 6 x 8 KB    weight tiles streamed by TMA: 48/64 rows x 64 K per slot (T1 tiles) or 2 x 96 rows x 64 K
+//                          over three slots (the N = 384 accumulate GEMMs run as two N = 192 UMMA groups)
 // CTAs work in PAIRS (cluster of 2, tcgen05 cta_group::2, UMMA M = 256): each CTA stages only half of
 // every weight tile, so the pair reads each weight byte once per 256 token rows (~28 B/clk/SM).
 // The only global traffic is the residual stream in and out (1.5 KB per token each way) + weights.
@@ -59,7 +60,7 @@ constexpr int THREADS = 64 + NSIMT * 32;
 // that 16 busy SIMT warps cannot starve the TMA / MMA issue loops.
 constexpr int W_TMA = NSIMT, W_MMA = NSIMT + 1;
 constexpr int SLOT = 8192;                  // ring slot: up to 64 rows x 128 B
-constexpr int SLOTS = 7;
+constexpr int SLOTS = 6;                    // T1 tiles take one slot per k-block, x-accumulate k-blocks three (2 x 96 rows)
 constexpr int QP = 104;                     // QKV row pitch in bf16 elements (96 + 8: conflict-free fragments)
 constexpr int OFF_XB = 0;                   // 6 k-block tiles of 16 KB
 constexpr int OFF_U = 98304;                // union: attention phase AO[2] + QKV | FFN phase FC[2]
@@ -322,6 +323,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* xb_ready = accx_full + 1;                   // leader's: x (TMEM) and XB rewritten by all warps of the pair
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256);
   int* seq_row = reinterpret_cast<int*>(tail + 320);    // [<= 130] first row of each sequence of this CTA's block
+  long long* issue_clk = reinterpret_cast<long long*>(tail + 896);   // [SLOTS] debug: clock of the TMA issue per slot
   float* stat_s = reinterpret_cast<float*>(tail + 1024);   // [NSIMT][32][2]
   float* lnp = reinterpret_cast<float*>(tail + 1024 + 4096);   // [3][384]: bias | gamma | beta of the next LayerNorm
 
@@ -364,28 +366,43 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (lane == 0) {
       // ================= TMA producer: this CTA's half of every weight tile, in MMA order =================
       int stage = 0;
-      uint32_t phase = 0;
-      auto load = [&](const CUtensorMap* tm, int c0, int c1, uint32_t bytes) {
-        mbar_wait(&empty[stage], phase ^ 1);
+      uint32_t ebits = 0;   // per slot: parity of its next `empty` wait (slots are not all used in every pass)
+      auto acquire = [&](int s) {
+        mbar_wait(&empty[s], ((ebits >> s) & 1u) ^ 1u);
+        ebits ^= 1u << s;
+      };
+      // one k-block of a T1 tile: this CTA's half (48 or 64 rows x 64 K) into one slot
+      auto load1 = [&](const CUtensorMap* tm, int c0, int c1, uint32_t bytes) {
+        acquire(stage);
         if (leader) mbar_expect_tx(&full[stage], 2u * bytes);
+        if constexpr (DBG) issue_clk[stage] = clock64();
         tma_load_2d_2sm(RING + stage * SLOT, tm, mapa_u32(smem_u32(&full[stage]), 0), c0, c1);
-        if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+        if (++stage == SLOTS) stage = 0;
+      };
+      // one k-block of an x-accumulate GEMM (N = 384 as two UMMA groups of 192): this CTA's 96 rows of each group
+      // into three consecutive slots (stage is 0 or 3 here: every tile takes a multiple of three slots)
+      auto load3 = [&](const CUtensorMap* tm, int c0, int c1) {
+        acquire(stage); acquire(stage + 1); acquire(stage + 2);
+        const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+        if (leader) mbar_expect_tx(&full[stage], 2u * 2u * 96u * 128u);
+        if constexpr (DBG) issue_clk[stage] = clock64();
+        tma_load_2d_2sm(RING + stage * SLOT, tm, bar, c0, c1);
+        tma_load_2d_2sm(RING + stage * SLOT + 96 * 128, tm, bar, c0, c1 + 192);
+        stage += 3;
+        if (stage == SLOTS) stage = 0;
       };
       const int r = static_cast<int>(rank);
       for (int bp = cluster_id; bp < n_pairs; bp += n_clusters) {
         for (int l = 0; l < a.layers; ++l) {
           auto emitQ = [&](int h) {
-            for (int kb = 0; kb < 6; ++kb) load(&tmQKV, kb * 64, l * 1152 + h * 96 + r * 48, 48 * 128);
+            for (int kb = 0; kb < 6; ++kb) load1(&tmQKV, kb * 64, l * 1152 + h * 96 + r * 48, 48 * 128);
           };
-          auto emitO = [&](int hp) {
-            for (int j = 0; j < 3; ++j) load(&tmWO, hp * 64, l * 384 + j * 128 + r * 64, 64 * 128);
-          };
+          auto emitO = [&](int hp) { load3(&tmWO, hp * 64, l * 384 + r * 96); };
           auto emitF1 = [&](int c) {
-            for (int kb = 0; kb < 6; ++kb) load(&tmW1, kb * 64, l * (a.n_chunks * 128) + c * 128 + r * 64, 64 * 128);
+            for (int kb = 0; kb < 6; ++kb) load1(&tmW1, kb * 64, l * (a.n_chunks * 128) + c * 128 + r * 64, 64 * 128);
           };
           auto emitF2 = [&](int c) {
-            for (int kb = 0; kb < 2; ++kb)
-              for (int j = 0; j < 3; ++j) load(&tmW2, c * 128 + kb * 64, l * 384 + j * 128 + r * 64, 64 * 128);
+            for (int kb = 0; kb < 2; ++kb) load3(&tmW2, c * 128 + kb * 64, l * 384 + r * 96);
           };
           emitQ(0);
           for (int h = 0; h < HEADS; ++h) {
@@ -405,6 +422,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // ================= MMA issuer (leader only; the WHOLE warp runs the loop, one elected lane issues) =================
       constexpr uint32_t idesc_q = make_idesc_bf16(256, 96);
       constexpr uint32_t idesc_n128 = make_idesc_bf16(256, 128);
+      constexpr uint32_t idesc_n192 = make_idesc_bf16(256, 192);
       const uint32_t xb_lo = sw128_desc_lo(smem_u32(XB));      // descriptor low words; +1024 per 16 KB tile
       const uint32_t ao_lo = sw128_desc_lo(smem_u32(AO));
       const uint32_t fc_lo = sw128_desc_lo(smem_u32(FC));
@@ -412,23 +430,36 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t d_x = tmem_base + TM_X;
       const uint32_t d_t1 = tmem_base + TM_T1;
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t fbits = 0;   // per slot: parity of its next `full` wait
       uint32_t n_t1 = 0, n_xb = 0;
       uint32_t ao_use[2] = {0, 0}, f_use[2] = {0, 0};
       PhaseAcc<DBG> pa;
       pa.start();
       if constexpr (DBG) { if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0) pa.ev = a.dbg + 512; }
+      long long lat_sum = 0, lat_n = 0, lat_max = 0, lat_all = 0, n_all = 0;
       auto slot_wait = [&]() -> uint32_t {
         pa.mark(3);
-        mbar_wait(&full[stage], phase);
+        bool waited = false;
+        const uint32_t par = (fbits >> stage) & 1u;
+        if constexpr (DBG) waited = !mbar_test_wait(&full[stage], par);
+        mbar_wait(&full[stage], par);
+        fbits ^= 1u << stage;
+        if constexpr (DBG) {   // latency issue -> landed, exact only when this thread had to wait for the slot
+          const long long lat = clock64() - *reinterpret_cast<volatile long long*>(&issue_clk[stage]);
+          lat_all += lat; ++n_all;
+          if (waited) { lat_sum += lat; ++lat_n; lat_max = lat > lat_max ? lat : lat_max; }
+        }
         pa.mark(2);
         tc_fence_after();
         return ring_lo + stage * (SLOT >> 4);
       };
-      auto slot_release = [&]() {
-        if (elect_one_sync()) umma_commit_2sm(&empty[stage]);
+      auto slot_release = [&](int n) {   // n consecutive slots become free once the MMAs issued so far have read them
+        if (elect_one_sync()) {
+          for (int i = 0; i < n; ++i) umma_commit_2sm(&empty[stage + i]);
+        }
         __syncwarp();
-        if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+        stage += n;
+        if (stage == SLOTS) stage = 0;
       };
       // T1 = XB[128 x 384] . Wtile^T (N = 96 or 128), overwriting T1
       auto issue_T1 = [&](uint32_t idesc) {
@@ -441,19 +472,20 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int kb = 0; kb < 6; ++kb) {
           const uint32_t b_lo = slot_wait();
           if (elect_one_sync()) umma_kblock_2sm(d_t1, xb_lo + kb * 1024, b_lo, idesc, static_cast<uint32_t>(kb != 0));
-          slot_release();
+          slot_release(1);
         }
         if (elect_one_sync()) umma_commit_2sm(t1_full);
         __syncwarp();
         pa.event(101);   // T1 tile issued
       };
-      // x[:, 0:384] += Atile[128 x 64] . W[384 x 64]^T as three N = 128 column groups
+      // x[:, 0:384] += Atile[128 x 64] . W[384 x 64]^T as two N = 192 column groups (B rows 0-95 | 96-191 of the 3-slot group)
       auto issue_X = [&](uint32_t a_lo) {
-        for (int j = 0; j < 3; ++j) {
-          const uint32_t b_lo = slot_wait();
-          if (elect_one_sync()) umma_kblock_2sm(d_x + j * 128, a_lo, b_lo, idesc_n128, 1u);
-          slot_release();
+        const uint32_t b_lo = slot_wait();
+        if (elect_one_sync()) {
+          umma_kblock_2sm(d_x, a_lo, b_lo, idesc_n192, 1u);
+          umma_kblock_2sm(d_x + 192, a_lo, b_lo + ((96 * 128) >> 4), idesc_n192, 1u);
         }
+        slot_release(3);
         pa.event(103);   // x-accumulate k-block issued
       };
       for (int bp = cluster_id; bp < n_pairs; bp += n_clusters) {
@@ -508,6 +540,9 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         pa.mark(3);
         if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0)
           for (int i = 0; i < 16; ++i) a.dbg[48 + i] = pa.a[i];
+        if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+          a.dbg[54] = lat_sum; a.dbg[55] = lat_n; a.dbg[56] = lat_max; a.dbg[57] = lat_all; a.dbg[58] = n_all;
+        }
       }
     }
   } else {

@@ -123,6 +123,9 @@ def main() -> None:
         print("MMA thread (clk):")
         for nm, v in zip(mma, s[48:54]):
             print(f"    {nm:22s} {int(v):>10d}")
+        if s[55] > 0:
+            print(f"ring: {int(s[58])} slots consumed; {int(s[55])} had to be waited for: TMA issue->landed latency mean {int(s[54] / s[55])} clk, "
+                  f"max {int(s[56])}; mean age of a slot when consumed {int(s[57] / max(s[58], 1))} clk")
         print("phase sums of other observers (clk): columns = leader w0, w15, w7, peer w0, w15, w7")
         for i, nm in enumerate(simt):
             print(f"    {nm:22s} " + " ".join(f"{int(s[1024 + k * 16 + i]):>9d}" for k in range(6)))
