@@ -288,6 +288,24 @@ def run_ours(args) -> None:
            "ms_per_step": e2e_s / args.steps * 1e3,
            "path": "owc_score(ids, targets in pinned host memory -> scores/idx/paired in host memory)"}
 
+    # ---- strings -> results (host tokenisation included; SURVEY 8d reports it beside the headline) ----
+    e2e_strings = None
+    if rank == 0:
+        tok = wl["tok"]
+        tok.encode_packed(wl["preds"][:4096])
+        t0 = time.perf_counter()
+        ids_s, cu_s = tok.encode_packed(wl["preds"])
+        t_tok = time.perf_counter() - t0
+        zc = sharded.broadcast_class_embeddings(eng, wl["cids"], wl["ccu"]) if world == 1 else None
+        if zc is not None:
+            t1 = time.perf_counter()
+            eng.score(ids_s, cu_s, zc, targets=wl["targets"], k=TOPK, out="host")
+            torch.cuda.synchronize()
+            t_sc = time.perf_counter() - t1
+            e2e_strings = {"value": rows / (t_tok + t_sc), "unit": "predictions/s", "tokenize_ms": t_tok * 1e3,
+                           "score_ms": t_sc * 1e3, "tokenizer": "native C++ WordPiece (owc_tokenize_packed)" if tok._native is not None
+                           else "tokenizers backend", "path": "strings -> WordPiece ids (host) -> owc_score -> results in host memory, one rank"}
+
     # ---- roofline leg: every launch bracketed by CUDA events on the engine's stream ----
     peaks, peak_src = load_peaks()
     eng.profile_begin()
@@ -334,6 +352,8 @@ def run_ours(args) -> None:
                    "parallelism": f"rows sharded x{world}; class embeddings broadcast; results gathered on rank 0"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
+    if e2e_strings is not None:
+        line["e2e_strings"] = e2e_strings
 
     if rank == 0 and not args.no_sim_leg:
         # north-star second metric: the fused similarity GEMM + top-k kernel alone at a 117k-name vocabulary

@@ -167,6 +167,24 @@ int32_t owc_debug_gemm_loop(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, in
  * already resident in device memory (CUDA events on the ctx stream); ms_per_launch out.          */
 int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, int32_t k, int32_t iters,
                              float* ms_per_launch);
+/* ---- host-side tokenisation (tokenisation stays on the host) --------------------
+ * Replaces the AutoTokenizer call of _text.py:193-195 for ASCII rows: BERT normaliser + pre-tokeniser + WordPiece
+ * + "[CLS] A [SEP]" (MPNet: "<s> A </s>") + truncation, multi-threaded, written straight into the packed layout
+ * owc_encode takes. Rows with a non-ASCII byte or a literal special token are FLAGGED (length -1) for the host
+ * library instead of being approximated. No CUDA involved.
+ *   vocab_bytes/vocab_offsets: n_vocab UTF-8 strings back to back + int64 offsets [n_vocab+1]; token i has id i.  */
+typedef struct owc_tokenizer owc_tokenizer;
+const char* owc_tokenizer_last_error(void);
+int32_t owc_tokenizer_create(const char* vocab_bytes, const int64_t* vocab_offsets, int32_t n_vocab, int32_t kind,
+                             int32_t max_length, owc_tokenizer** out);
+int32_t owc_tokenizer_destroy(owc_tokenizer* tok);
+/*   text_bytes/text_offsets: n rows as one byte blob + int64 offsets [n+1]; ids_out: int32 [ids_capacity]
+ *   (total bytes + 2n always suffices), rows back to back in row order; lens_out: int32 [n], tokens per row or -1
+ *   for a flagged row (which contributes nothing to ids_out); n_ids_out: ids written; n_threads <= 0: all cores.  */
+int32_t owc_tokenize_packed(const owc_tokenizer* tok, const char* text_bytes, const int64_t* text_offsets, int64_t n,
+                            int32_t n_threads, int32_t* ids_out, int64_t ids_capacity, int32_t* lens_out,
+                            int64_t* n_ids_out);
+
 /* Debug: timeline of the block-resident fused encoder kernel (enc_fused.cuh). When the ctx was created with
  * OWC_FUSED_DBG=1 in the environment, the first SIMT thread of CTA 0 records clock64 at: block start,
  * residual rows loaded, then per layer: attention block done, LayerNorm 1 done, feed-forward done,

@@ -64,6 +64,10 @@ EXPORTS = {
     "owc_debug_gemm_loop": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_bench_sim_kernel": (_I32, [_P, _I64, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_debug_fused_stamps": (_I32, [_P, _P]),
+    "owc_tokenizer_last_error": (C.c_char_p, []),
+    "owc_tokenizer_create": (_I32, [_P, _P, _I32, _I32, _I32, C.POINTER(_P)]),
+    "owc_tokenizer_destroy": (_I32, [_P]),
+    "owc_tokenize_packed": (_I32, [_P, _P, _P, _I64, _I32, _P, _I64, _P, C.POINTER(_I64)]),
 }
 
 _lib = None

@@ -10,9 +10,12 @@ every kernel is padding-invariant, so pad-to-longest would only add work.
 
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import numpy as np
 
-__all__ = ["HostTokenizer", "pack_ids"]
+__all__ = ["HostTokenizer", "NativeWordPiece", "pack_ids"]
 
 
 def pack_ids(seqs: list[list[int]]) -> tuple[np.ndarray, np.ndarray]:
@@ -26,8 +29,57 @@ def pack_ids(seqs: list[list[int]]) -> tuple[np.ndarray, np.ndarray]:
     return ids, cu.astype(np.int32)
 
 
+class NativeWordPiece:
+    """The library's multi-threaded C++ WordPiece (``csrc/tokenizer.cpp``; ``owc_tokenize_packed``).
+
+    Handles ASCII rows exactly as the BERT tokenizer does and writes the packed layout directly; rows it
+    flags (non-ASCII bytes, literal special tokens) are left to the caller's fallback tokenizer."""
+
+    def __init__(self, vocab: list[str], kind: str, max_length: int) -> None:
+        from . import _cabi
+
+        self._lib = _cabi.lib()
+        enc = [w.encode("utf-8") for w in vocab]
+        offs = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc)), out=offs[1:])
+        blob = b"".join(enc)
+        self._h = C.c_void_p()
+        rc = self._lib.owc_tokenizer_create(blob, offs.ctypes.data, len(enc), 0 if kind == "bert" else 1, int(max_length),
+                                            C.byref(self._h))
+        if rc != 0:
+            raise _cabi.OwcError(self._lib.owc_tokenizer_last_error().decode("utf-8", "replace"))
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            if self._h:
+                self._lib.owc_tokenizer_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def tokenize(self, texts: list[str], threads: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """``(ids of the unflagged rows back to back, lens int32 [n] with -1 for flagged rows)``."""
+        from . import _cabi
+
+        n = len(texts)
+        enc = [t.encode("utf-8") for t in texts]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.int64, count=n), out=offs[1:])
+        blob = b"".join(enc)
+        cap = int(offs[-1]) + 2 * n + 1
+        ids = np.empty(cap, dtype=np.int32)
+        lens = np.empty(n, dtype=np.int32)
+        n_ids = C.c_int64(0)
+        rc = self._lib.owc_tokenize_packed(self._h, blob, offs.ctypes.data, n, int(threads), ids.ctypes.data, cap,
+                                           lens.ctypes.data, C.byref(n_ids))
+        if rc != 0:
+            raise _cabi.OwcError(self._lib.owc_tokenizer_last_error().decode("utf-8", "replace"))
+        return ids[: n_ids.value], lens
+
+
 class HostTokenizer:
-    """WordPiece tokenizer over an in-memory vocabulary (``tokenizers`` Rust backend)."""
+    """WordPiece tokenizer over an in-memory vocabulary: the library's native C++ path for ASCII rows
+    (``NativeWordPiece``), the ``tokenizers`` backend for everything else and as the cross-check."""
 
     def __init__(self, vocab: list[str], kind: str = "bert", max_length: int = 512) -> None:
         from tokenizers import Tokenizer, normalizers, pre_tokenizers, processors
@@ -61,12 +113,45 @@ class HostTokenizer:
         self.cls_id = table[cls]
         self.sep_id = table[sep]
         self.vocab_size = len(vocab)
+        self._native = None
+        if os.environ.get("OWC_NATIVE_TOK", "1") != "0":
+            try:
+                self._native = NativeWordPiece(vocab, kind, max_length)
+            except Exception:       # library not built yet (CPU-only checkout): the backend below does all rows
+                self._native = None
 
     def encode_ragged(self, texts: list[str]) -> list[list[int]]:
         if not isinstance(texts, list):
             raise NotImplementedError
         return [e.ids for e in self._tok.encode_batch(texts)]
 
-    def encode_packed(self, texts: list[str]) -> tuple[np.ndarray, np.ndarray]:
+    def encode_packed(self, texts: list[str], native: bool | None = None) -> tuple[np.ndarray, np.ndarray]:
         """Strings -> ``(ids_packed, cu_seqlens)`` ready for ``owc_encode``."""
-        return pack_ids(self.encode_ragged(texts))
+        if not isinstance(texts, list):
+            raise NotImplementedError
+        use_native = self._native is not None if native is None else (native and self._native is not None)
+        if not use_native or not texts:
+            return pack_ids(self.encode_ragged(texts))
+        ids, lens = self._native.tokenize(texts)
+        flagged = np.nonzero(lens < 0)[0]
+        if flagged.size == 0:
+            cu = np.zeros(len(texts) + 1, dtype=np.int64)
+            np.cumsum(lens, out=cu[1:])
+            if cu[-1] >= 2**31:
+                raise ValueError("packed batch exceeds 2^31 tokens; split it")
+            return ids, cu.astype(np.int32)
+        # splice the rows the native path left to the backend (non-ASCII, literal special tokens) back in
+        extra = self.encode_ragged([texts[i] for i in flagged])
+        lens = lens.astype(np.int64)
+        lens[flagged] = [len(e) for e in extra]
+        cu = np.zeros(len(texts) + 1, dtype=np.int64)
+        np.cumsum(lens, out=cu[1:])
+        if cu[-1] >= 2**31:
+            raise ValueError("packed batch exceeds 2^31 tokens; split it")
+        out = np.empty(int(cu[-1]), dtype=np.int32)
+        is_extra = np.zeros(len(texts), dtype=bool)
+        is_extra[flagged] = True
+        tok_extra = np.repeat(is_extra, lens)
+        out[~tok_extra] = ids
+        out[tok_extra] = np.fromiter((t for e in extra for t in e), dtype=np.int32, count=int(tok_extra.sum()))
+        return out, cu.astype(np.int32)
