@@ -127,3 +127,21 @@ def concept_semantic_similarity(items: list, encode, extract=simple_concepts, re
     if reduce == "min":
         return torch.stack([r.min() for r in rows]).mean().item()
     return list(zip(concepts, [r.tolist() for r in rows], strict=True))
+
+
+def ranking_game_scores(encode, matches: list[dict], threshold: float = 0.05):
+    """``eval_ranking.py:192-237`` restated: three encodes, two paired dots (``torch.bmm`` on ``[N,1,D] x [N,D,1]``),
+    difference thresholded at 0.05 -> 1 / 0.5 / 0. ``encode(list[str]) -> torch.Tensor [n, D]``.
+    Returns ``(scores list[float], sim_a, sim_b)``. Test infrastructure only."""
+    import torch
+
+    refs_z = encode([m["reference"] for m in matches]).unsqueeze(1)
+    a_z = encode([m["player_a_response"] for m in matches]).unsqueeze(2)
+    b_z = encode([m["player_b_response"] for m in matches]).unsqueeze(2)
+    a_scores = torch.bmm(refs_z, a_z).squeeze()
+    b_scores = torch.bmm(refs_z, b_z).squeeze()
+    diff = a_scores - b_scores
+    scores = torch.zeros_like(diff) + 0.5
+    scores[diff > threshold] = 1
+    scores[diff < -threshold] = 0
+    return scores.tolist(), a_scores, b_scores

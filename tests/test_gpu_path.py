@@ -200,3 +200,28 @@ def test_full_size_properties_c2(minilm, eng_minilm):
     clear = margin.numpy() >= 1e-3
     agree = res["idx"][sample, 0] == i_ref[:, 0].numpy()
     assert agree[clear].all() and agree.mean() >= 0.9
+
+
+def test_ranking_criterion_on_gpu(minilm):
+    """eval_ranking.py:192-237 through the host mirror on the GPU vs the oracle restatement of the same lines."""
+    import random
+
+    from owc_b200.ranking import semantic_similarity_game_scores
+
+    b = minilm
+    T.configure(b.arch, b.sd, b.vocab, device=0)
+    try:
+        rng = random.Random(3)
+        cls = [str(s) for s in b.gold["class_names"]]
+        preds = [str(s) for s in b.gold["preds"]]
+        games = [{"reference": (ref := rng.choice(cls)), "player_a_response": rng.choice([ref, rng.choice(preds)]),
+                  "player_b_response": rng.choice([ref, rng.choice(preds), ref + " " + rng.choice(b.words)])}
+                 for _ in range(2000)]
+        got, sa, sb = semantic_similarity_game_scores(games, return_similarities=True)
+        want, wa, wb = metrics_ref.ranking_game_scores(
+            lambda texts: encoder_ref.encode_strings(b.sd, b.arch, b.hf_tok, list(texts)), games)
+        assert np.abs(sa - wa.numpy()).max() < 1e-2 and np.abs(sb - wb.numpy()).max() < 1e-2
+        far = np.abs(np.abs(wa.numpy() - wb.numpy()) - 0.05) > 2e-3
+        assert far.mean() > 0.9 and np.array_equal(np.asarray(got)[far], np.asarray(want)[far])
+    finally:
+        T.reset()

@@ -244,3 +244,39 @@ def test_eval_metrics_cli_roundtrip(oracle_backed, tmp_path, capsys):
     assert f"{'model-a':<29}: {float(gold.mean()):.3f}" in text
     with pytest.raises(KeyError):
         EM.score_file(str(f), ["bleu"])
+
+
+def _games(bundle, n, seed=3):
+    import random
+
+    rng = random.Random(seed)
+    cls = [str(s) for s in bundle.gold["class_names"]]
+    preds = [str(s) for s in bundle.gold["preds"]]
+    players = ["model_a", "model_b", "model_c"]
+    out = []
+    for _ in range(n):
+        ref = rng.choice(cls)
+        a, b = rng.sample(players, 2)
+        out.append({"reference": ref, "player_a_name": a, "player_b_name": b,
+                    "player_a_response": rng.choice([ref, rng.choice(preds), ref + " " + rng.choice(bundle.words)]),
+                    "player_b_response": rng.choice([ref, rng.choice(preds)])})
+    return out
+
+
+def test_ranking_criterion_matches_oracle(oracle_backed):
+    """eval_ranking.py:192-237 (semantic_similarity criterion) through the host mirror vs the oracle restatement."""
+    from oracle import metrics_ref
+    from owc_b200.ranking import semantic_similarity_game_scores
+
+    b = oracle_backed
+    games = _games(b, 300)
+    got, sa, sb = semantic_similarity_game_scores(games, return_similarities=True)
+    want, wa, wb = metrics_ref.ranking_game_scores(
+        lambda texts: encoder_ref.encode_strings(b.sd, b.arch, b.hf_tok, list(texts)), games)
+    assert np.abs(sa - wa.numpy()).max() < 1e-5 and np.abs(sb - wb.numpy()).max() < 1e-5
+    far = np.abs(np.abs(wa.numpy() - wb.numpy()) - 0.05) > 1e-4       # decisions away from the threshold are identical
+    assert np.array_equal(np.asarray(got)[far], np.asarray(want)[far])
+    assert set(got) <= {0.0, 0.5, 1.0} and {0.5} <= set(got)            # identical responses draw
+    assert semantic_similarity_game_scores([]) == []
+    with pytest.raises(ValueError):
+        semantic_similarity_game_scores([{"reference": "x", "player_a_response": "y"}])
