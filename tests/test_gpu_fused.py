@@ -142,3 +142,23 @@ def test_score_through_fused_encoder(minilm, engines):
     margin = p["scores"][:, 0] - p["scores"][:, 1]
     clear = margin >= 1e-3
     assert (f["idx"][clear, 0] == p["idx"][clear, 0]).all()
+
+
+def test_pipelined_strings_to_results_equals_one_call(minilm, engines):
+    from owc_b200.pipeline import score_strings_pipelined
+
+    fused, _ = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    cls = synth.real_class_names("food101")
+    preds, targets = synth.make_predictions(9000, cls, minilm.words, seed=21)
+    preds[17] = "café " + preds[17]            # a row the native tokenizer hands to the backend
+    cids, ccu = tok.encode_packed(cls)
+    zc = fused.encode(cids, ccu, out="device")
+    t = np.asarray(targets, np.int32)
+    pids, pcu = tok.encode_packed(preds)
+    one = fused.score(pids, pcu, zc, targets=t, k=5)
+    many = score_strings_pipelined(fused, tok, preds, zc, targets=t, k=5, chunk_rows=2000)
+    assert np.array_equal(one["idx"], many["idx"])
+    assert np.abs(one["scores"] - many["scores"]).max() < 1e-6 and np.abs(one["paired"] - many["paired"]).max() < 1e-6
+    empty = score_strings_pipelined(fused, tok, [], zc, k=5)
+    assert empty["scores"].shape == (0, 5) and empty["paired"] is None
