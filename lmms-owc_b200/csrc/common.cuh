@@ -350,6 +350,78 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
   return d;
 }
+// One lane of a fully active warp (always the same one), so a whole warp can run the issue loop with
+// warp-uniform control flow and operands (kept in uniform registers) and only the issue is predicated.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Low word of make_sw128_kmajor_desc (start address >> 4, LBO = 1); the high word is the constant below.
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kSw128DescHi = 0x40004040u;   // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+// The four K = 16 steps of one 64-wide k-block (A and B advance 32 B per step: start field + 2), cta_group::2.
+__device__ __forceinline__ void umma_kblock_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, pt;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p0;\n\t"
+      "add.u32 ta, %1, 2;\n\t"
+      "add.u32 tb, %2, 2;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ta, %1, 4;\n\t"
+      "add.u32 tb, %2, 4;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ta, %1, 6;\n\t"
+      "add.u32 tb, %2, 6;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi)
+      : "memory");
+}
+// The four K = 16 steps of one 64-wide k-block (A and B advance 32 B per step: start field + 2), cta_group::1.
+__device__ __forceinline__ void umma_kblock_1sm(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, pt;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p0;\n\t"
+      "add.u32 ta, %1, 2;\n\t"
+      "add.u32 tb, %2, 2;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ta, %1, 4;\n\t"
+      "add.u32 tb, %2, 4;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ta, %1, 6;\n\t"
+      "add.u32 tb, %2, 6;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi)
+      : "memory");
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 // (InstrDescriptor: c_format [4,6)=1 F32, a_format [7,10)=1 BF16, b_format [10,13)=1 BF16,
 //  a_major bit 15 = 0, b_major bit 16 = 0, n>>3 [17,23), m>>4 [24,29).)

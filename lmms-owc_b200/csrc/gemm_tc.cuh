@@ -479,13 +479,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    {
+      // ---------------- MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues ----------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       if constexpr (ARES) {
         mbar_wait(afull, 0);
         tc_fence_after();
       }
+      const uint32_t tiles_lo = sw128_desc_lo(smem_u32(tiles));
+      const uint32_t ares_lo = sw128_desc_lo(smem_u32(ares));
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -497,22 +499,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
-          if (t == 0 && kb == 0) OWC_STAMP(2);
+          if (t == 0 && kb == 0 && lane == 0) OWC_STAMP(2);
           tc_fence_after();
-          const uint32_t s_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t a_addr = ARES ? smem_u32(ares + kb * Cfg::A_BYTES) : s_addr;
-          const uint32_t b_addr = ARES ? s_addr : s_addr + Cfg::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(d_tmem, make_sw128_kmajor_desc(a_addr + k * 32), make_sw128_kmajor_desc(b_addr + k * 32),
-                     idesc, static_cast<uint32_t>((kb | k) != 0));
+          const uint32_t s_lo = tiles_lo + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
+          const uint32_t a_lo = ARES ? ares_lo + static_cast<uint32_t>(kb * (Cfg::A_BYTES >> 4)) : s_lo;
+          const uint32_t b_lo = ARES ? s_lo : s_lo + (Cfg::A_BYTES >> 4);
+          if (elect_one_sync()) {
+            umma_kblock_1sm(d_tmem, a_lo, b_lo, idesc, static_cast<uint32_t>(kb != 0));
+            umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
           }
-          umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[buf]);  // accumulator complete
+        if (elect_one_sync()) umma_commit(&tfull[buf]);  // accumulator complete
+        __syncwarp();
       }
-      OWC_STAMP(3);
+      if (lane == 0) OWC_STAMP(3);
     }
   } else if constexpr (EPI == EPI_RES_LN) {
     // ---------------- fused residual + LayerNorm epilogue (all 8 epilogue warps) ----------------
@@ -658,13 +660,15 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader only): UMMA 256 x BN x 16 across the pair ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader only, whole warp, one elected lane): UMMA 256 x BN x 16 across the pair ----------------
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
       if constexpr (ARES) {
         mbar_wait(afull, 0);
         tc_fence_after();
       }
+      const uint32_t tiles_lo = sw128_desc_lo(smem_u32(tiles));
+      const uint32_t ares_lo = sw128_desc_lo(smem_u32(ares));
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -677,18 +681,18 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t s_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t a_addr = ARES ? smem_u32(ares + kb * Cfg::A_BYTES) : s_addr;
-          const uint32_t b_addr = ARES ? s_addr : s_addr + Cfg::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_2sm(d_tmem, make_sw128_kmajor_desc(a_addr + k * 32), make_sw128_kmajor_desc(b_addr + k * 32),
-                         idesc, static_cast<uint32_t>((kb | k) != 0));
+          const uint32_t s_lo = tiles_lo + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
+          const uint32_t a_lo = ARES ? ares_lo + static_cast<uint32_t>(kb * (Cfg::A_BYTES >> 4)) : s_lo;
+          const uint32_t b_lo = ARES ? s_lo : s_lo + (Cfg::A_BYTES >> 4);
+          if (elect_one_sync()) {
+            umma_kblock_2sm(d_tmem, a_lo, b_lo, idesc, static_cast<uint32_t>(kb != 0));
+            umma_commit_2sm(&empty[stage]);  // multicast: frees the stage in both CTAs
           }
-          umma_commit_2sm(&empty[stage]);  // multicast: frees the stage in both CTAs
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull[buf]);      // multicast: accumulator complete in both CTAs
+        if (elect_one_sync()) umma_commit_2sm(&tfull[buf]);      // multicast: accumulator complete in both CTAs
+        __syncwarp();
       }
     }
   } else {
