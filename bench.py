@@ -317,7 +317,7 @@ def run_ours(args) -> None:
         t_all = time.perf_counter() - t1
         e2e_strings = {"value": rows / t_all, "unit": "predictions/s", "ms_per_step": t_all * 1e3, "tokenize_alone_ms": t_tok * 1e3,
                        "tokenizer": "native C++ WordPiece (owc_tokenize_packed)" if tok._native is not None else "tokenizers backend",
-                       "path": "strings -> WordPiece ids on a host thread, overlapped with owc_score of the previous 25k-row chunk "
+                       "path": "strings -> WordPiece ids on a host thread, overlapped with owc_score of the previous 20k-row chunk "
                                "-> results in host memory (owc_b200.pipeline.score_strings_pipelined), one rank"}
 
     # ---- roofline leg: every launch bracketed by CUDA events on the engine's stream ----

@@ -208,10 +208,27 @@ extern "C" int32_t owc_tokenizer_destroy(owc_tokenizer* t) {
 extern "C" int32_t owc_tokenize_packed(const owc_tokenizer* t, const char* text_bytes, const int64_t* text_offsets, int64_t n,
                                        int32_t n_threads, int32_t* ids_out, int64_t ids_capacity, int32_t* lens_out,
                                        int64_t* n_ids_out) {
-  if (!t || !text_offsets || !lens_out || !n_ids_out || n < 0 || (n > 0 && (!text_bytes || !ids_out)))
+  if (!t || !lens_out || !n_ids_out || n < 0 || (n > 0 && (!text_bytes || !ids_out)))
     return tfail("owc_tokenize_packed: bad argument");
   *n_ids_out = 0;
   if (n == 0) return 0;
+  // text_offsets == NULL: the rows are separated by single NUL bytes (n - 1 separators; the caller guarantees that no
+  // row contains a NUL itself - the host joins the strings in one call instead of encoding them one by one)
+  std::vector<int64_t> own_offsets;
+  if (!text_offsets) {
+    own_offsets.reserve(static_cast<size_t>(n) + 1);
+    own_offsets.push_back(0);
+    const char* p = text_bytes;
+    for (int64_t r = 0; r + 1 < n; ++r) {
+      const char* q = p + strlen(p);
+      own_offsets.push_back(q - text_bytes);   // end of row r == position of its separator
+      p = q + 1;
+    }
+    own_offsets.push_back((p - text_bytes) + static_cast<int64_t>(strlen(p)));
+    // rows r >= 1 start one byte after the previous row's end: keep one offset array by treating the separator as
+    // the first byte of the next row - NUL is a dropped character for the tokenizer, so the result is unchanged
+    text_offsets = own_offsets.data();
+  }
   int threads = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
   threads = std::max(1, std::min(threads, 32));
   if (n < 4096) threads = 1;

@@ -18,7 +18,7 @@ __all__ = ["score_strings_pipelined"]
 
 
 def score_strings_pipelined(engine, tokenizer, predictions: list[str], zc_device, targets=None, k: int = 1,
-                            chunk_rows: int = 25_000, precision: str | None = None) -> dict:
+                            chunk_rows: int = 20_000, precision: str | None = None) -> dict:
     """Tokenise + encode + match ``predictions`` against class embeddings ``zc_device`` (CUDA fp32 ``[C, H]``).
 
     Returns numpy ``{"scores" [n,k], "idx" [n,k], "paired" [n] or None}`` in the original row order.
@@ -46,18 +46,23 @@ def score_strings_pipelined(engine, tokenizer, predictions: list[str], zc_device
 
     worker = threading.Thread(target=producer, daemon=True)
     worker.start()
+    parts = []
     try:
         for _ in bounds:
             item = ready.get()
             if isinstance(item, BaseException):
                 raise item
             lo, hi, (ids, cu) = item
-            res = engine.score(ids, cu, zc_device, targets=None if tg is None else tg[lo:hi], k=k, precision=precision,
-                               out="host")
-            out["scores"][lo:hi] = res["scores"]
-            out["idx"][lo:hi] = res["idx"]
-            if tg is not None:
-                out["paired"][lo:hi] = res["paired"]
+            # results stay on the device: the call returns as soon as the launches are queued, so the device never
+            # waits for the host between chunks; one copy at the end brings everything back
+            parts.append((lo, hi, engine.score(ids, cu, zc_device, targets=None if tg is None else tg[lo:hi], k=k,
+                                               precision=precision, out="device")))
     finally:
         worker.join(timeout=60)
+    engine.sync()   # also raises if a chunk carried an out-of-vocabulary id
+    for lo, hi, res in parts:
+        out["scores"][lo:hi] = res["scores"].cpu().numpy()
+        out["idx"][lo:hi] = res["idx"].cpu().numpy()
+        if tg is not None:
+            out["paired"][lo:hi] = res["paired"].cpu().numpy()
     return out
