@@ -162,3 +162,32 @@ def test_pipelined_strings_to_results_equals_one_call(minilm, engines):
     assert np.abs(one["scores"] - many["scores"]).max() < 1e-6 and np.abs(one["paired"] - many["paired"]).max() < 1e-6
     empty = score_strings_pipelined(fused, tok, [], zc, k=5)
     assert empty["scores"].shape == (0, 5) and empty["paired"] is None
+
+
+def test_config4_scale_properties(minilm, engines):
+    """BASELINE config 4 shape: a 117k-name vocabulary encoded by the fused kernel, predictions matched with the fused
+    top-5; checked through size-independent properties and against an exact fp32 product of the same embeddings."""
+    import torch
+
+    fused, _ = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    names = synth.make_class_names(117_000, minilm.words, seed=1234)
+    assert len(set(names)) == len(names)
+    preds, targets = synth.make_predictions(6000, names, minilm.words, seed=9)
+    cids, ccu = tok.encode_packed(names)
+    zc = fused.encode(cids, ccu, out="device")
+    assert zc.shape == (117_000, 384) and torch.isfinite(zc).all()
+    assert (zc.norm(dim=1) - 1).abs().max().item() < 1e-5
+    pids, pcu = tok.encode_packed(preds)
+    t = np.asarray(targets, np.int32)
+    res = fused.score(pids, pcu, zc, targets=t, k=5, want_embeds=True)
+    assert (np.diff(res["scores"], axis=1) <= 0).all()
+    assert (res["scores"][:, 0] >= res["paired"] - 1e-6).all()
+    zp = torch.from_numpy(res["embeds"]).cuda()
+    exact = zp @ zc.T                                   # 6000 x 117000 fp32 on the device, test only
+    top_s, top_i = torch.topk(exact, 2, dim=1)
+    assert (torch.from_numpy(res["scores"][:, 0]).cuda() - top_s[:, 0]).abs().max().item() < 1e-4
+    clear = ((top_s[:, 0] - top_s[:, 1]) >= 1e-3).cpu().numpy()
+    assert (res["idx"][clear, 0] == top_i[:, 0].cpu().numpy()[clear]).all()
+    paired = exact[torch.arange(len(preds), device="cuda"), torch.from_numpy(t).long().cuda()].cpu().numpy()
+    assert np.abs(res["paired"] - paired).max() < 1e-4

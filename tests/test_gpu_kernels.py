@@ -129,3 +129,26 @@ def test_sim_topk_rejects_bad_k(tiny_engine):
 def test_sim_kernel_bench_hook_runs(tiny_engine):
     ms = tiny_engine.bench_sim_kernel(4096, 1000, 384, 5, 3)
     assert ms > 0
+
+
+def test_sim_topk_at_the_117k_vocabulary(tiny_engine):
+    """BASELINE config 4 scale: 117 000 class rows (WordNet-noun scale), fused top-5, against exact fp64 scores
+    computed in row slabs (the n x c matrix is never held in one piece here either)."""
+    n, c, d, k = 1536, 117_000, 384, 5
+    zp, zc = _unit_rows(n, d, 11, spread=0.5), _unit_rows(c, d, 12, spread=0.5)
+    scores, idx = tiny_engine.sim_topk(zp.cuda(), zc.cuda(), k, precision="bf16")
+    torch.cuda.synchronize()
+    scores, idx = scores.cpu().numpy(), idx.cpu().numpy()
+    assert (np.diff(scores, axis=1) <= 0).all() and idx.min() >= 0 and idx.max() < c
+    zc64 = zc.double()
+    for lo in range(0, n, 256):
+        s = zp[lo:lo + 256].double() @ zc64.T
+        top_s, top_i = torch.topk(s, k + 1, dim=1)
+        got_s, got_i = scores[lo:lo + 256], idx[lo:lo + 256]
+        # returned scores are exact dot products of the returned classes
+        assert np.abs(np.take_along_axis(s.numpy(), got_i.astype(np.int64), 1) - got_s).max() < 2e-6
+        # wherever rank j and rank j+1 are separated by more than the bf16 candidate noise, rank j is identical
+        gap = (top_s[:, :k] - top_s[:, 1:]).numpy()
+        clear = gap >= 1e-3
+        assert (got_i[clear] == top_i[:, :k].numpy()[clear]).all()
+        assert np.abs(got_s[:, 0] - top_s[:, 0].numpy()).max() < 1e-3
