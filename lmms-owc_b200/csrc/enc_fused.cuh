@@ -61,15 +61,15 @@ constexpr int THREADS = 64 + NSIMT * 32;
 constexpr int W_TMA = NSIMT, W_MMA = NSIMT + 1;
 constexpr int SLOT = 8192;                  // ring slot: up to 64 rows x 128 B
 constexpr int SLOTS = 6;                    // T1 tiles take one slot per k-block, x-accumulate k-blocks three (2 x 96 rows)
-constexpr int QP = 104;                     // QKV row pitch in bf16 elements (96 + 8: conflict-free fragments)
+constexpr int QROW = 192;                   // bytes of one QKV row: q | k | v of one head, 16-byte chunks XOR-swizzled inside each 64 B third
 constexpr int OFF_XB = 0;                   // 6 k-block tiles of 16 KB
 constexpr int OFF_U = 98304;                // union: attention phase AO[2] + QKV | FFN phase FC[2]
-constexpr int OFF_AO = OFF_U;               // 2 x 16384
-constexpr int OFF_QKV = OFF_U + 32768;      // 128 x 208 = 26624
+constexpr int OFF_AO = OFF_U;               // one head-pair tile of 16384
+constexpr int OFF_QKV = OFF_U + 16384;      // 2 x (128 x 192) = 2 x 24576: one buffer per SIMT group
 constexpr int OFF_FC = OFF_U;               // 2 x 32768
 constexpr int OFF_RING = OFF_U + 65536;     // 163840
 constexpr int OFF_TAIL = OFF_RING + SLOTS * SLOT;   // 221184
-constexpr int TAIL_BYTES = 1024 + 4096 + 3 * 384 * 4;   // barriers / tables, LayerNorm statistics, LayerNorm bias|gamma|beta
+constexpr int TAIL_BYTES = 1024 + 4096 + 3 * 384 * 4 + 3 * 384 * 4;   // barriers / tables, LayerNorm statistics, LayerNorm bias|gamma|beta, QKV bias
 constexpr int SMEM_BYTES = OFF_TAIL + TAIL_BYTES + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t TM_X = 0, TM_T1 = 384;   // TMEM column offsets
@@ -123,15 +123,22 @@ __device__ __forceinline__ void store_a_chunk32(uint8_t* tiles, int r, int k, co
   }
 }
 
-// One (sequence, head) of the block: q|k|v rows in `qkv` (pitch QP), output into the AO tile (A-operand
-// layout, 16-byte chunks cb..cb+3 of each 128-byte row). Same arithmetic as attn_pair (attn_mma.cuh).
-template <int TP>
-__device__ __forceinline__ void attn_head_smem(const __nv_bfloat16* qkv, uint8_t* ao_tile, int beg, int T, int lane, int cb,
-                                               float scale_log2) {
-  constexpr int P = fz::QP;
+// Address of 16-byte chunk `c` (0-3 q, 4-7 k, 8-11 v) of QKV row `row`: rows are 192 B apart and the chunk index is
+// XORed inside its 64-byte third with (row >> 1) & 3, which keeps every access pattern of the attention body
+// (32-bit fragment loads of 8 rows x 4 lanes, ldmatrix rows, 16-byte row stores) free of bank conflicts.
+__device__ __forceinline__ const uint8_t* qkv_chunk(const uint8_t* qkv, int row, int c) {
+  return qkv + row * fz::QROW + (((c & 12) | ((c & 3) ^ ((row >> 1) & 3))) << 4);
+}
+
+// One (sequence, head) of the block: q|k|v rows in `qkv`, output into the AO tile (A-operand layout, 16-byte chunks
+// cb..cb+3 of each 128-byte row). Same arithmetic as attn_pair (attn_mma.cuh). `pre_store` runs before the first
+// write to the AO tile (it waits until the O-projection that last read the tile has completed).
+template <int TP, typename PreStore>
+__device__ __forceinline__ void attn_head_smem(const uint8_t* qkv, uint8_t* ao_tile, int beg, int T, int lane, int cb,
+                                               float scale_log2, PreStore pre_store) {
   constexpr int NT = TP / 8, MT = TP / 16, DN = 4;
   const int g = lane >> 2, t4 = lane & 3;
-  auto rowp = [&](int i) { return qkv + min(beg + i, 127) * P; };   // rows past the block are never used unmasked
+  auto row_of = [&](int i) { return min(beg + i, 127); };   // rows past the block are never used unmasked
 #pragma unroll 1
   for (int mt = 0; mt < MT; ++mt) {
     if (mt * 16 >= T) break;
@@ -139,22 +146,21 @@ __device__ __forceinline__ void attn_head_smem(const __nv_bfloat16* qkv, uint8_t
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { s[nt][0] = 0.f; s[nt][1] = 0.f; s[nt][2] = 0.f; s[nt][3] = 0.f; }
     const int r0 = mt * 16 + g, r1 = r0 + 8;
-    const __nv_bfloat16* q0 = rowp(r0);
-    const __nv_bfloat16* q1 = rowp(r1);
+    const int qr0 = row_of(r0), qr1 = row_of(r1);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t af[4];
-      af[0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + t4 * 2);
-      af[1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + t4 * 2);
-      af[2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8 + t4 * 2);
-      af[3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8 + t4 * 2);
+      af[0] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr0, 2 * ks) + t4 * 4);
+      af[1] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr1, 2 * ks) + t4 * 4);
+      af[2] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr0, 2 * ks + 1) + t4 * 4);
+      af[3] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr1, 2 * ks + 1) + t4 * 4);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         if (nt * 8 < T) {   // warp-uniform
-          const __nv_bfloat16* kr = rowp(nt * 8 + g) + 32;
+          const int kr = row_of(nt * 8 + g);
           uint32_t bf[2];
-          bf[0] = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + t4 * 2);
-          bf[1] = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8 + t4 * 2);
+          bf[0] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, kr, 4 + 2 * ks) + t4 * 4);
+          bf[1] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, kr, 5 + 2 * ks) + t4 * 4);
           mma_bf16_16816(s[nt], af, bf);
         }
       }
@@ -209,11 +215,11 @@ __device__ __forceinline__ void attn_head_smem(const __nv_bfloat16* qkv, uint8_t
     for (int kt = 0; kt < MT; ++kt) {
       if (kt * 16 < T) {   // warp-uniform
         const uint32_t af[4] = {pk[2 * kt][0], pk[2 * kt][1], pk[2 * kt + 1][0], pk[2 * kt + 1][1]};
-        const __nv_bfloat16* vrow = rowp(kt * 16 + (lane & 15)) + 64;
+        const int vr = row_of(kt * 16 + (lane & 15));
 #pragma unroll
         for (int dn = 0; dn < DN; ++dn) {
           uint32_t bf[2];
-          ldmatrix_x2_trans(bf, vrow + dn * 8);
+          ldmatrix_x2_trans(bf, qkv_chunk(qkv, vr, 8 + dn));
           mma_bf16_16816(o[dn], af, bf);
         }
       }
@@ -221,6 +227,7 @@ __device__ __forceinline__ void attn_head_smem(const __nv_bfloat16* qkv, uint8_t
     float inv0, inv1;   // sums are >= 1 (the row maximum contributes 2^0): the approximate reciprocal is exact enough
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(sum0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(sum1));
+    pre_store();
     const int gr0 = beg + r0, gr1 = beg + r1;
     if (r0 < T) {
       uint8_t* p0 = ao_tile + gr0 * 128 + t4 * 4;
@@ -272,11 +279,12 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* tail = base + OFF_TAIL;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [SLOTS]  leader's: both CTAs' TMA bytes of the slot landed
   uint64_t* empty = full + SLOTS;                       // [SLOTS]  per CTA (multicast commit): slot consumed
-  uint64_t* t1_full = empty + SLOTS;                    // per CTA (multicast commit): T1 accumulator complete
-  uint64_t* t1_free = t1_full + 1;                      // leader's: all 2*NSIMT warps have drained T1
-  uint64_t* ao_full = t1_free + 1;                      // [2] leader's: AO tile written by all warps of the pair
-  uint64_t* ao_free = ao_full + 2;                      // [2] per CTA (commit): O-projection has read the tile
-  uint64_t* f_full = ao_free + 2;                       // [2] leader's
+  uint64_t* t1_full = empty + SLOTS;                    // [2] per CTA (multicast commit): T1 tile n complete -> t1_full[n & 1]
+  uint64_t* t1_free_a = t1_full + 2;                    // leader's: the draining GROUP (8 warps per CTA) has read T1 (attention phase)
+  uint64_t* t1_free_f = t1_free_a + 1;                  // leader's: all 2*NSIMT warps have read T1 (feed-forward phase)
+  uint64_t* ao_full = t1_free_f + 1;                    // leader's: both heads of a pair written to AO by all warps of the pair
+  uint64_t* ao_free = ao_full + 1;                      // per CTA (commit): the O-projection has read AO
+  uint64_t* f_full = ao_free + 1;                       // [2] leader's
   uint64_t* f_free = f_full + 2;                        // [2] per CTA (commit)
   uint64_t* accx_full = f_free + 2;                     // per CTA (commit): residual accumulator complete
   uint64_t* xb_ready = accx_full + 1;                   // leader's: x (TMEM) and XB rewritten by all warps of the pair
@@ -285,6 +293,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   long long* issue_clk = reinterpret_cast<long long*>(tail + 896);   // [SLOTS] debug: clock of the TMA issue per slot
   float* stat_s = reinterpret_cast<float*>(tail + 1024);   // [NSIMT][32][2]
   float* lnp = reinterpret_cast<float*>(tail + 1024 + 4096);   // [3][384]: bias | gamma | beta of the next LayerNorm
+  float* bqkv_s = lnp + 3 * 384;                               // [3][384]: q | k | v projection bias of the current layer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -300,11 +309,13 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     for (int s = 0; s < SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(t1_full, 1);
-    mbar_init(t1_free, 2 * NSIMT);
+    mbar_init(&t1_full[0], 1);
+    mbar_init(&t1_full[1], 1);
+    mbar_init(t1_free_a, NSIMT);            // 2 CTAs x NSIMT/2 warps of the draining group
+    mbar_init(t1_free_f, 2 * NSIMT);
+    mbar_init(ao_full, 2 * NSIMT);
+    mbar_init(ao_free, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&ao_full[b], 2 * NSIMT);
-      mbar_init(&ao_free[b], 1);
       mbar_init(&f_full[b], 2 * NSIMT);
       mbar_init(&f_free[b], 1);
     }
@@ -366,8 +377,9 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           emitQ(0);
           for (int h = 0; h < HEADS; ++h) {
             if (h + 1 < HEADS) emitQ(h + 1);
-            if (h & 1) emitO(h >> 1);
+            if (h >= 2 && (h & 1) == 0) emitO((h - 2) >> 1);
           }
+          emitO(HEADS / 2 - 1);
           emitF1(0);
           for (int c = 0; c < a.n_chunks; ++c) {
             if (c + 1 < a.n_chunks) emitF1(c + 1);
@@ -391,7 +403,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       int stage = 0;
       uint32_t fbits = 0;   // per slot: parity of its next `full` wait
       uint32_t n_t1 = 0, n_xb = 0;
-      uint32_t ao_use[2] = {0, 0}, f_use[2] = {0, 0};
+      uint32_t n_ao = 0, f_use[2] = {0, 0};
       PhaseAcc<DBG> pa;
       pa.start();
       if constexpr (DBG) { if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0) pa.ev = a.dbg + 512; }
@@ -420,21 +432,26 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         stage += n;
         if (stage == SLOTS) stage = 0;
       };
-      // T1 = XB[128 x 384] . Wtile^T (N = 96 or 128), overwriting T1
-      auto issue_T1 = [&](uint32_t idesc) {
+      // T1 = XB[128 x 384] . Wtile^T (N = 96 or 128), overwriting T1. Tile n completes on t1_full[n & 1]; before it is
+      // issued the previous tile must have been drained: by one SIMT group (attention phase) or by all warps (FFN)
+      uint32_t n_free_a = 0, n_free_f = 0;
+      int pending = 0;   // 0 none, 1 attention tile, 2 feed-forward tile
+      auto issue_T1 = [&](uint32_t idesc, int kind) {
         pa.mark(3);
-        mbar_wait(t1_free, (n_t1 & 1) ^ 1);   // previous T1 tile drained by every SIMT warp of the pair
+        if (pending == 1) { mbar_wait(t1_free_a, n_free_a & 1); ++n_free_a; }
+        else if (pending == 2) { mbar_wait(t1_free_f, n_free_f & 1); ++n_free_f; }
+        pending = kind;
         pa.mark(1);
         pa.event(100);   // t1_free observed
         tc_fence_after();
-        ++n_t1;
         for (int kb = 0; kb < 6; ++kb) {
           const uint32_t b_lo = slot_wait();
           if (elect_one_sync()) umma_kblock_2sm(d_t1, xb_lo + kb * 1024, b_lo, idesc, static_cast<uint32_t>(kb != 0));
           slot_release(1);
         }
-        if (elect_one_sync()) umma_commit_2sm(t1_full);
+        if (elect_one_sync()) umma_commit_2sm(&t1_full[n_t1 & 1]);
         __syncwarp();
+        ++n_t1;
         pa.event(101);   // T1 tile issued
       };
       // x[:, 0:384] += Atile[128 x 64] . W[384 x 64]^T as two N = 192 column groups (B rows 0-95 | 96-191 of the 3-slot group)
@@ -455,21 +472,24 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           mbar_wait(xb_ready, n_xb & 1); ++n_xb;
           pa.mark(0);
           tc_fence_after();
-          issue_T1(idesc_q);
+          // O-projection of head pair p (heads 2p by SIMT group 0, 2p+1 by group 1) goes out behind Q(2p+3): by then
+          // group 1 is finishing head 2p+1 and the issuer never sits on ao_full while a Q tile could be issued
+          auto issue_O = [&]() {
+            pa.mark(3);
+            mbar_wait(ao_full, n_ao & 1); ++n_ao;
+            pa.mark(4);
+            pa.event(102);   // ao_full observed
+            tc_fence_after();
+            issue_X(ao_lo);
+            if (elect_one_sync()) umma_commit_2sm(ao_free);
+            __syncwarp();
+          };
+          issue_T1(idesc_q, 1);
           for (int h = 0; h < HEADS; ++h) {
-            if (h + 1 < HEADS) issue_T1(idesc_q);
-            if (h & 1) {
-              const int b = (h >> 1) & 1;
-              pa.mark(3);
-              mbar_wait(&ao_full[b], ao_use[b] & 1); ++ao_use[b];
-              pa.mark(4);
-              pa.event(102);   // ao_full observed
-              tc_fence_after();
-              issue_X(ao_lo + b * 1024);
-              if (elect_one_sync()) umma_commit_2sm(&ao_free[b]);
-              __syncwarp();
-            }
+            if (h + 1 < HEADS) issue_T1(idesc_q, 1);
+            if (h >= 2 && (h & 1) == 0) issue_O();
           }
+          issue_O();
           if (elect_one_sync()) umma_commit_2sm(accx_full);
           __syncwarp();
           // ---- feed-forward block ----
@@ -477,9 +497,9 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           mbar_wait(xb_ready, n_xb & 1); ++n_xb;
           pa.mark(0);
           tc_fence_after();
-          issue_T1(idesc_n128);
+          issue_T1(idesc_n128, 2);
           for (int c = 0; c < a.n_chunks; ++c) {
-            if (c + 1 < a.n_chunks) issue_T1(idesc_n128);
+            if (c + 1 < a.n_chunks) issue_T1(idesc_n128, 2);
             const int b = c & 1;
             pa.mark(3);
             mbar_wait(&f_full[b], f_use[b] & 1); ++f_use[b];
@@ -517,7 +537,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
     };
     uint32_t n_t1 = 0, n_accx = 0;
-    uint32_t ao_use[2] = {0, 0}, f_use[2] = {0, 0};
+    uint32_t n_pair = 0, f_use[2] = {0, 0};   // head pairs this warp has contributed to; uses of the two FC buffers
     const bool stamp = DBG && a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     int n_stamp = 0;
     PhaseAcc<DBG> pa;
@@ -547,12 +567,13 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // NW warps of a lane quadrant each own every NW-th 32-column chunk and exchange partial statistics.
     // Shared memory left to the L1 by this kernel is ~0, so every __ldg is an L2 round trip: the parameters of the
     // next LayerNorm are staged in shared memory at the start of the phase that ends with it.
-    auto stage_ln_params = [&](const float* bias, const float* gamma, const float* beta) {
+    auto stage_ln_params = [&](const float* bias, const float* gamma, const float* beta, const float* qkv_bias) {
       named_bar_sync(1, NSIMT * 32);   // the previous LayerNorm's readers are done
       const int i = threadIdx.x;
       if (i < 3 * (H / 4)) {
         const float* src = (i < H / 4) ? bias : (i < 2 * (H / 4) ? gamma : beta);
         reinterpret_cast<float4*>(lnp)[i] = __ldg(reinterpret_cast<const float4*>(src) + (i % (H / 4)));
+        if (qkv_bias != nullptr) reinterpret_cast<float4*>(bqkv_s)[i] = __ldg(reinterpret_cast<const float4*>(qkv_bias) + i);
       }
     };
     auto layer_norm = [&](bool to_global, float* gout) {
@@ -675,85 +696,90 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if constexpr (DBG) pa.tracing = (bp == cluster_id && l == 1);
         const size_t lo = static_cast<size_t>(l) * static_cast<size_t>(a.layer_stride);
         // =========== attention block ===========
-        stage_ln_params(a.bo + lo, a.ln1g + lo, a.ln1b + lo);
-        const float* bqkv = a.bqkv + lo;
-        for (int h = 0; h < HEADS; ++h) {
-          // ---- drain T1 = [q|k|v] of head h: + bias -> bf16 rows in QKV ----
-          constexpr int CP = 96 / NW;   // columns per warp
-          float4 bq[CP / 4];            // this warp's bias slice, fetched while the MMAs of the tile still run
+        stage_ln_params(a.bo + lo, a.ln1g + lo, a.ln1b + lo, a.bqkv + lo);
+        named_bar_sync(1, NSIMT * 32);   // staged QKV bias visible to both groups
+        // The 16 SIMT warps work as two groups of 8 on alternating heads (group g: heads g, g+2, ...): while one
+        // group runs the attention of head h out of its own QKV buffer, the other drains and converts head h+1,
+        // so a head costs the tensor pipe's Q tile, not the drain + attention chain. Each group covers all four
+        // TMEM lane quadrants with two warps (48 of the 96 columns each).
+        {
+          const int grp = warp_e >> 3;                 // SIMT group of this warp
+          const int gw = warp_e & 7;                   // warp inside the group
+          const int gpart = (warp_e >> 2) & 1;         // which 48 columns of T1 this warp drains
+          uint8_t* qkv_g = reinterpret_cast<uint8_t*>(QKV) + grp * (128 * QROW);
+          for (int h = grp; h < HEADS; h += 2) {
+            // ---- drain T1 = [q|k|v] of head h: + bias -> bf16 rows in this group's QKV buffer ----
+            constexpr int CP = 48;      // columns per warp
+            const uint32_t tile = n_t1 + static_cast<uint32_t>(h);     // global index of this T1 tile
+            pa.mark(15);
+            mbar_wait(&t1_full[tile & 1], (tile >> 1) & 1);
+            pa.mark(0);
+            pa.event(0);   // t1_full observed (attention)
+            tc_fence_after();
+            uint32_t v[CP];
+            if (!(a.ablate & 8)) {
+              tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(gpart * CP), v);
+            } else {
 #pragma unroll
-          for (int i = 0; i < CP / 8; ++i) {
-            const int col = part * CP + i * 8;                        // 8 columns never straddle q|k|v
-            const float* bp8 = bqkv + (col >> 5) * H + h * D + (col & 31);
-            bq[2 * i] = __ldg(reinterpret_cast<const float4*>(bp8));
-            bq[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(bp8) + 1);
-          }
-          pa.mark(15);
-          mbar_wait(t1_full, n_t1 & 1); ++n_t1;
-          pa.mark(0);
-          pa.event(0);   // t1_full observed (attention)
-          tc_fence_after();
-          uint32_t v[CP];
-          if (!(a.ablate & 8)) {
-            tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(part * CP), v);
-          } else {
-#pragma unroll
-            for (int i = 0; i < CP; ++i) v[i] = 0;
-          }
-          tmem_ld_wait_regs(v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_leader(t1_free);
-          pa.mark(1);
-          pa.event(1);   // T1 drained, t1_free sent
-          {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(QKV) + r * (QP * 2) + part * CP * 2;
+              for (int i = 0; i < CP; ++i) v[i] = 0;
+            }
+            tmem_ld_wait_regs(v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_leader(t1_free_a);
+            pa.mark(1);
+            pa.event(1);   // T1 drained, t1_free sent
 #pragma unroll
             for (int i = 0; i < CP / 8; ++i) {
-              const float4 b0 = bq[2 * i], b1 = bq[2 * i + 1];
+              const int col = gpart * CP + i * 8;                       // 8 columns never straddle q|k|v
+              const float4* bp8 = reinterpret_cast<const float4*>(bqkv_s + (col >> 5) * H + h * D + (col & 31));
+              const float4 b0 = bp8[0], b1 = bp8[1];
               uint4 w;
               w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x, __uint_as_float(v[8 * i + 1]) + b0.y);
               w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + b0.z, __uint_as_float(v[8 * i + 3]) + b0.w);
               w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + b1.x, __uint_as_float(v[8 * i + 5]) + b1.y);
               w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + b1.z, __uint_as_float(v[8 * i + 7]) + b1.w);
-              *reinterpret_cast<uint4*>(dst + i * 16) = w;
+              *reinterpret_cast<uint4*>(const_cast<uint8_t*>(qkv_chunk(qkv_g, r, gpart * 6 + i))) = w;
             }
-          }
-          pa.mark(2);
-          named_bar_sync(1, NSIMT * 32);   // every row of the head is in QKV
-          pa.mark(3);
-          pa.event(2);   // QKV rows complete (after barrier)
-          // ---- attention of this head for the block's sequences ----
-          const int tb = (h >> 1) & 1;
-          if ((h & 1) == 0) { mbar_wait(&ao_free[tb], (ao_use[tb] & 1) ^ 1); }   // O-projection of the tile's previous use is done
-          uint8_t* ao_tile = AO + tb * 16384;
-          const int cb = (h & 1) * 4;
-          for (int i = warp_e; i < ((a.ablate & 1) ? 0 : nseq); i += NSIMT) {
-            const int beg = seq_row[i];
-            const int T = seq_row[i + 1] - beg;
-            if (T <= 0) continue;
-            if (T <= 16) attn_head_smem<16>(QKV, ao_tile, beg, T, lane, cb, a.scale_log2);
-            else if (T <= 32) attn_head_smem<32>(QKV, ao_tile, beg, T, lane, cb, a.scale_log2);
-            else attn_head_smem<64>(QKV, ao_tile, beg, T, lane, cb, a.scale_log2);
-          }
-          pa.mark(4);
-          pa.event(3);   // own attention done
-          if (h & 1) {
+            pa.mark(2);
+            named_bar_sync(6 + grp, (NSIMT / 2) * 32);   // every row of the head is in this group's QKV buffer
+            pa.mark(3);
+            pa.event(2);   // QKV rows complete (after barrier)
+            // ---- attention of this head for the block's sequences (sequence i -> warp i % 8 of the group) ----
+            const int cb = (h & 1) * 4;
+            bool ao_ok = false;
+            auto pre_store = [&]() {   // the O-projection of the previous head pair has read the AO tile
+              if (!ao_ok) { mbar_wait(ao_free, (n_pair & 1) ^ 1); ao_ok = true; }
+            };
+            for (int i = gw; i < ((a.ablate & 1) ? 0 : nseq); i += NSIMT / 2) {
+              const int beg = seq_row[i];
+              const int T = seq_row[i + 1] - beg;
+              if (T <= 0) continue;
+              if (T <= 16) attn_head_smem<16>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+              else if (T <= 32) attn_head_smem<32>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+              else attn_head_smem<64>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+            }
+            pa.mark(4);
+            pa.event(3);   // own attention done
+            // A warp without sequences must not run ahead either: its arrival for THIS pair may only be counted once
+            // the previous pair's phase of ao_full has completed (ao_free is committed behind that O-projection)
+            pre_store();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) arrive_leader(&ao_full[tb]);
-            ++ao_use[tb];
+            if (lane == 0) arrive_leader(ao_full);   // 2 * NSIMT arrivals per head pair: each group's warps for its head
+            ++n_pair;
+            named_bar_sync(6 + grp, (NSIMT / 2) * 32);   // this group's QKV buffer is rewritten by its next head
+            pa.mark(5);
+            pa.event(4);   // head done (after barrier)
           }
-          named_bar_sync(1, NSIMT * 32);   // QKV is rewritten by the next head
-          pa.mark(5);
-          pa.event(4);   // head done (after barrier)
+          n_t1 += HEADS;
         }
         FZ_STAMP();
         layer_norm(false, nullptr);
         publish_x();
         FZ_STAMP();
         // =========== feed-forward block ===========
-        stage_ln_params(a.b2 + lo, a.ln2g + lo, a.ln2b + lo);
+        stage_ln_params(a.b2 + lo, a.ln2g + lo, a.ln2b + lo, nullptr);
         const float* b1p = a.b1 + lo;
         for (int c = 0; c < a.n_chunks; ++c) {
           constexpr int CP = 128 / NW;   // columns per warp
@@ -761,7 +787,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
           for (int i = 0; i < CP / 4; ++i) bf1[i] = __ldg(reinterpret_cast<const float4*>(b1p + c * 128 + part * CP) + i);
           pa.mark(15);
-          mbar_wait(t1_full, n_t1 & 1); ++n_t1;
+          mbar_wait(&t1_full[n_t1 & 1], (n_t1 >> 1) & 1); ++n_t1;
           pa.mark(10);
           pa.event(10);   // t1_full observed (FFN)
           tc_fence_after();
@@ -775,7 +801,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tmem_ld_wait_regs(v);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) arrive_leader(t1_free);
+          if (lane == 0) arrive_leader(t1_free_f);
           pa.mark(11);
           pa.event(11);   // drained
           const int fb = c & 1;

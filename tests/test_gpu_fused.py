@@ -191,3 +191,20 @@ def test_config4_scale_properties(minilm, engines):
     assert (res["idx"][clear, 0] == top_i[:, 0].cpu().numpy()[clear]).all()
     paired = exact[torch.arange(len(preds), device="cuda"), torch.from_numpy(t).long().cuda()].cpu().numpy()
     assert np.abs(res["paired"] - paired).max() < 1e-4
+
+
+@pytest.mark.parametrize("seed,lo,hi", [(0, 1, 65), (1, 1, 9), (2, 30, 65), (3, 60, 65), (4, 1, 3), (5, 10, 40)])
+def test_random_length_mixes_are_deterministic_and_match(minilm, engines, seed, lo, hi):
+    """Blocks with very few or very many sequences put different numbers of warps to work in the kernel's two
+    attention groups; results must not depend on warp timing (two runs are bit-identical) and match the per-GEMM path."""
+    fused, plain = engines
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(lo, hi, size=int(40000 / ((lo + hi) / 2)))
+    ids = rng.integers(5, minilm.arch.vocab, size=int(lens.sum())).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    z1 = fused.encode(ids, cu)
+    z2 = fused.encode(ids, cu)
+    assert np.array_equal(z1, z2)
+    assert np.isfinite(z1).all()
+    zp = plain.encode(ids, cu)
+    assert np.abs(z1 - zp).max() < 1e-3
