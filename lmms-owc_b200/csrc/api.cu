@@ -66,7 +66,7 @@ struct owc_ctx {
   // tcgen05 kernel variant: 0 = one CTA per 128 rows, 1 = CTA pairs (cta_group::2), 2 = CTA pairs + resident A.
   // Measured on B200: the encoder's short sweeps (2-8 column tiles per row block) run fastest on the 1-CTA
   // kernel, the similarity sweep (hundreds of tiles) on pairs with the A block resident.
-  int gemm_mode = 0;       // encoder contractions (env OWC_GEMM_MODE)
+  int gemm_mode = -1;      // encoder contractions (env OWC_GEMM_MODE); -1 = by width: 1-CTA for H < 768, CTA pairs from H = 768
   int sim_mode = 2;        // similarity + top-k     (env OWC_SIM_MODE)
   int fuse_ln = 1;         // fuse residual+LayerNorm into the O-proj / FFN2 epilogue (env OWC_FUSE_LN)
   int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
@@ -307,8 +307,11 @@ template <int BN, int EPI, int KC>
 static int launch_gemm(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb_full, const CUtensorMap& tb_half,
                        const CUtensorMap& tc, const GemmArgs& g) {
   const int splits = pick_splits(c, g.M, g.N, BN);
-  if (c->gemm_mode == 0) return launch_gemm_tc<BN, EPI, KC>(c, ta, tb_full, tc, g, splits);
-  if (c->gemm_mode == 2 && g.K <= kAresMaxK) return launch_gemm_tc2<BN, EPI, KC, true>(c, ta, tb_half, tc, g, splits);
+  // measured on B200: the short sweeps of a 384-wide encoder (2-8 column tiles per row block) run fastest on the 1-CTA
+  // kernel; from H = 768 (12-16 tile sweeps, K up to 3072) the halved weight traffic of CTA pairs wins (+7 % GEMM rate)
+  const int mode = c->gemm_mode >= 0 ? c->gemm_mode : ((g.K >= 768 || g.N >= 2304) ? 1 : 0);
+  if (mode == 0) return launch_gemm_tc<BN, EPI, KC>(c, ta, tb_full, tc, g, splits);
+  if (mode == 2 && g.K <= kAresMaxK) return launch_gemm_tc2<BN, EPI, KC, true>(c, ta, tb_half, tc, g, splits);
   return launch_gemm_tc2<BN, EPI, KC, false>(c, ta, tb_half, tc, g, splits);
 }
 
@@ -725,7 +728,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
   const int ln_grid = (M + 7) / 8;
   // The residual+LayerNorm tail is fused into the O-projection / FFN2 epilogue when a whole row fits
   // the two TMEM accumulator buffers (H == 2 * kEncBN, i.e. the MiniLM width) and the 1-CTA kernel runs.
-  const bool fuse_ln = bf && H == 2 * kEncBN && c->gemm_mode == 0 && c->fuse_ln;
+  const bool fuse_ln = bf && H == 2 * kEncBN && c->gemm_mode <= 0 && c->fuse_ln;
   for (int l = 0; l < a.layers; ++l) {
     const LayerW& L = e->layers[l];
     const bool last = l + 1 == a.layers;
@@ -1150,7 +1153,7 @@ extern "C" int32_t owc_debug_gemm(owc_ctx* c, const float* a, const float* w, co
   OWC_TRY(ensure(c, c->tmp_b, static_cast<size_t>(n) * kdim * 2));
   OWC_TRY(launch_convert(c, a, static_cast<__nv_bfloat16*>(c->tmp_a.p), static_cast<long long>(m) * kdim));
   OWC_TRY(launch_convert(c, w, static_cast<__nv_bfloat16*>(c->tmp_b.p), static_cast<long long>(n) * kdim));
-  if (tile_n == 0) tile_n = kEncBN + 1000 * c->gemm_mode;
+  if (tile_n == 0) tile_n = kEncBN + 1000 * std::max(c->gemm_mode, 0);
   const int variant = tile_n / 1000;   // 0: 1-CTA, 1: CTA pair, 2: CTA pair + resident A
   const int bn = tile_n % 1000;
   if (variant == 2 && kdim > 384) return fail("resident-A variant needs kdim <= 384");

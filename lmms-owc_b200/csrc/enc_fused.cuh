@@ -12,8 +12,9 @@
 //         cols [384, 512)  T1: the transient accumulator - one head's [q|k|v] (96 cols) or one
 //                          128-wide slice of the FFN intermediate.
 //   SMEM  XB  96 KB        bf16 copy of x in UMMA K-major SWIZZLE_128B layout (A operand of QKV / FFN1)
-//         QKV 26 KB        current head's q|k|v rows (bf16, 208 B pitch) for the mma.sync attention
-//         AO  2 x 16 KB    attention output of a head PAIR as A operand (K = 64) of the O-projection
+//         QKV 2 x 24 KB    one head's q|k|v rows (bf16, 192 B rows, XOR-swizzled 16-byte chunks) for the mma.sync
+//                          attention - one buffer per SIMT group (the two groups alternate heads)
+//         AO  16 KB        attention output of a head PAIR as A operand (K = 64) of the O-projection
 //         FC  2 x 32 KB    GELU(FFN1 slice) as A operand (K = 128) of FFN2 (aliases QKV/AO)
 //         RING 6 x 8 KB    weight tiles streamed by TMA: 48/64 rows x 64 K per slot (T1 tiles) or 2 x 96 rows x 64 K
 //                          over three slots (the N = 384 accumulate GEMMs run as two N = 192 UMMA groups)
@@ -23,8 +24,10 @@
 //
 // Roles per CTA: warps 0..15 = SIMT warps (TMEM drains, bias/GELU/LayerNorm, attention), warp 16 lane 0 = TMA
 // producer (its half of every tile), warp 17 of the LEADER = MMA issuer for the pair (uniform loop, elected lane).
-// MMA issue order keeps the tensor pipe busy while the SIMT warps work on the previous tile:
-//   attention block:  Q(0) Q(1) | Q(2) O(0) | Q(3) Q(4) O(1) ...   (O(p) = heads 2p, 2p+1, K = 64)
+// In the attention block the SIMT warps form two groups of 8 that alternate heads: while group g runs the attention
+// of head h out of its QKV buffer, the other group drains and converts head h+1.
+// MMA issue order keeps the tensor pipe busy while the SIMT warps work on the previous tiles:
+//   attention block:  Q(0) Q(1) Q(2) Q(3) O(0) Q(4) Q(5) O(1) ...   (O(p) = heads 2p, 2p+1, K = 64)
 //   feed-forward:     F1(0) F1(1) F2(0) F1(2) F2(1) ...
 // Reference semantics: transformers modeling_bert.py:114-207 (self-attention + output LayerNorm),
 // :287-356 (intermediate GELU + output LayerNorm), post-LN residual blocks.
