@@ -208,3 +208,35 @@ def test_random_length_mixes_are_deterministic_and_match(minilm, engines, seed, 
     assert np.isfinite(z1).all()
     zp = plain.encode(ids, cu)
     assert np.abs(z1 - zp).max() < 1e-3
+
+
+def test_other_depth_and_ffn_width(monkeypatch):
+    """The fused kernel is generic in depth and FFN width (multiples of 128): 3 layers, FFN 1152 (an ODD number of
+    128-wide slices, which exercises the alternating accumulator barriers) against the per-GEMM path and the oracle."""
+    from oracle.hf_models import build_hf_tokenizer, build_model
+    from owc_b200 import arch as A
+
+    arch = A.EncoderArch("bert-3x1152", A.KIND_BERT, layers=3, hidden=384, heads=12, inter=1152, vocab=4096,
+                         max_pos=512, type_vocab=2, ln_eps=1e-12)
+    vocab = synth.build_vocab("bert", arch.vocab)
+    words = synth.vocab_words(vocab)
+    model = build_model(arch)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    tok = HostTokenizer(vocab, "bert")
+    texts = _ragged_texts(words, 2500, 13, lo=1, hi=20)
+    ids, cu = tok.encode_packed(texts)
+    assert np.diff(cu).max() <= 64
+    monkeypatch.setenv("OWC_FUSED", "1")
+    fused = Engine(arch, sd, device=0)
+    monkeypatch.setenv("OWC_FUSED", "0")
+    plain = Engine(arch, sd, device=0)
+    try:
+        zf, nf = _launches(fused, lambda: fused.encode(ids, cu))
+        zp = plain.encode(ids, cu)
+        assert nf <= 3                                   # embed + fused + pool
+        assert np.abs(zf - zp).max() < 1e-3
+        want = encoder_ref.encode_strings(sd, arch, build_hf_tokenizer(arch, vocab), texts[:300]).numpy()
+        assert np.abs(zf[:300] - want).max() < 1e-3
+    finally:
+        fused.close()
+        plain.close()
