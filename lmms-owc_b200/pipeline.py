@@ -59,10 +59,15 @@ def score_strings_pipelined(engine, tokenizer, predictions: list[str], zc_device
                                                precision=precision, out="device")))
     finally:
         worker.join(timeout=60)
-    engine.sync()   # also raises if a chunk carried an out-of-vocabulary id
+    if hasattr(engine, "sync"):
+        engine.sync()   # also raises if a chunk carried an out-of-vocabulary id
+
+    def host(x):
+        return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
     for lo, hi, res in parts:
-        out["scores"][lo:hi] = res["scores"].cpu().numpy()
-        out["idx"][lo:hi] = res["idx"].cpu().numpy()
+        out["scores"][lo:hi] = host(res["scores"])
+        out["idx"][lo:hi] = host(res["idx"])
         if tg is not None:
-            out["paired"][lo:hi] = res["paired"].cpu().numpy()
+            out["paired"][lo:hi] = host(res["paired"])
     return out

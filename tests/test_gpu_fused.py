@@ -240,3 +240,34 @@ def test_other_depth_and_ffn_width(monkeypatch):
     finally:
         fused.close()
         plain.close()
+
+
+def test_multi_task_sweep_equals_per_file_scoring(minilm, engines):
+    """BASELINE config 5 in miniature: several models' prediction files over several tasks; the sweep (one class
+    encode per task, files concatenated) returns what scoring every file on its own returns."""
+    from owc_b200.sweep import score_sweep
+
+    fused, _ = engines
+    tok = HostTokenizer(minilm.vocab, "bert")
+    tasks = {}
+    for ti, ds in enumerate(("caltech101", "dtd", "eurosat", "oxford_pets")):
+        names = synth.real_class_names(ds)
+        files = {}
+        for mi in range(3):
+            preds, targets = synth.make_predictions(700 + 150 * mi, names, minilm.words, seed=100 * ti + mi)
+            files[f"model{mi}"] = {"predictions": preds, "targets": targets}
+        tasks[ds] = {"class_names": names, "files": files}
+    tasks["empty_task"] = {"class_names": ["a", "b", "c", "d", "e"], "files": {}}
+    got = score_sweep(fused, tok, tasks, k=5)
+    assert set(got) == set(tasks) and got["empty_task"] == {}
+    for ds, spec in tasks.items():
+        if not spec["files"]:
+            continue
+        cids, ccu = tok.encode_packed(spec["class_names"])
+        zc = fused.encode(cids, ccu, out="device")
+        for key, f in spec["files"].items():
+            pids, pcu = tok.encode_packed(f["predictions"])
+            one = fused.score(pids, pcu, zc, targets=np.asarray(f["targets"], np.int32), k=5)
+            assert np.array_equal(one["idx"], got[ds][key]["idx"]), (ds, key)
+            assert np.abs(one["scores"] - got[ds][key]["scores"]).max() < 1e-6
+            assert np.abs(one["paired"] - got[ds][key]["paired"]).max() < 1e-6

@@ -280,3 +280,36 @@ def test_ranking_criterion_matches_oracle(oracle_backed):
     assert semantic_similarity_game_scores([]) == []
     with pytest.raises(ValueError):
         semantic_similarity_game_scores([{"reference": "x", "player_a_response": "y"}])
+
+
+def test_sweep_groups_files_by_class_set(oracle_backed):
+    """score_sweep's grouping / cutting logic on CPU (oracle-backed engine: encode + a torch top-k stand-in)."""
+    from owc_b200.sweep import score_sweep
+
+    b = oracle_backed
+
+    class Eng(OracleEngine):
+        def encode(self, ids, cu, out="host", precision=None):
+            z = super().encode(ids, cu)
+            return torch.from_numpy(z) if out == "device" else z
+
+        def score(self, ids, cu, zc, targets=None, k=1, precision=None, out="host", want_embeds=False):
+            zp = torch.from_numpy(OracleEngine.encode(self, ids, cu))
+            s, i, _ = encoder_ref.sim_topk(zp, zc, k)
+            paired = None if targets is None else (zp * zc[torch.from_numpy(np.asarray(targets)).long()]).sum(1).numpy()
+            return {"scores": s.numpy(), "idx": i.numpy().astype(np.int32), "paired": paired, "embeds": None}
+
+    eng = Eng(b)
+    tok = HostTokenizer(b.vocab, "bert")
+    cls = [str(s) for s in b.gold["class_names"]]
+    preds = [str(s) for s in b.gold["preds"]]
+    tg = b.gold["targets"].tolist()
+    tasks = {"t1": {"class_names": cls, "files": {"m0": {"predictions": preds[:40], "targets": tg[:40]},
+                                                   "m1": {"predictions": preds[40:100], "targets": tg[40:100]}}},
+             "t2": {"class_names": cls[:10], "files": {"m0": {"predictions": preds[:25], "targets": None}}}}
+    got = score_sweep(eng, tok, tasks, k=3)
+    assert got["t1"]["m0"]["idx"].shape == (40, 3) and got["t1"]["m1"]["idx"].shape == (60, 3)
+    assert got["t2"]["m0"]["paired"] is None and got["t2"]["m0"]["scores"].shape == (25, 3)
+    assert np.abs(got["t1"]["m1"]["paired"] - b.gold["paired_scores"][40:100]).max() < 1e-5   # the reference's own scores
+    with pytest.raises(ValueError):
+        score_sweep(eng, tok, {"t": {"class_names": cls[:2], "files": {"m": {"predictions": ["x"], "targets": None}}}}, k=3)

@@ -1,0 +1,52 @@
+"""BASELINE config 5 for the record: 13 models x the reference's 10 classification tasks (real class names, test-split
+sizes from the reference's split files, synthetic predictions) re-scored in one run on one GPU.
+Usage: python tools/sweep_bench.py [n_models]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import owc_b200  # noqa: E402,F401
+from owc_b200 import arch as A, synth  # noqa: E402
+from owc_b200.engine import Engine  # noqa: E402
+from owc_b200.sweep import score_sweep  # noqa: E402
+from owc_b200.tokenizer import HostTokenizer  # noqa: E402
+from owc_b200.weights import random_state_dict  # noqa: E402
+
+TEST_ROWS = {"caltech101": 2465, "dtd": 1692, "eurosat": 8100, "fgvc_aircraft": 3333, "flowers102": 2463,
+             "food101": 30300, "oxford_pets": 3669, "stanford_cars": 8041, "sun397": 19850, "ucf101": 3783}
+
+n_models = int(sys.argv[1]) if len(sys.argv) > 1 else 13
+arch = A.MINILM_L6
+vocab = synth.build_vocab("bert", arch.vocab)
+words = synth.vocab_words(vocab)
+tok = HostTokenizer(vocab, "bert")
+eng = Engine(arch, random_state_dict(arch), device=0)
+tasks = {}
+for ti, (ds, rows) in enumerate(TEST_ROWS.items()):
+    # FGVC-Aircraft's 100 variant names live in the downloaded dataset (variants.txt), not in the reference repo
+    names = synth.make_class_names(100, words, seed=77) if ds == "fgvc_aircraft" else synth.real_class_names(ds)
+    files = {}
+    for m in range(n_models):
+        preds, targets = synth.make_predictions(rows, names, words, seed=1000 * ti + m)
+        files[f"model{m:02d}"] = {"predictions": preds, "targets": targets}
+    tasks[ds] = {"class_names": names, "files": files}
+total = sum(len(f["predictions"]) for t in tasks.values() for f in t["files"].values())
+score_sweep(eng, tok, {k: v for k, v in list(tasks.items())[:2]}, k=5)      # warm-up
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+res = score_sweep(eng, tok, tasks, k=5)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+acc = {ds: float(np.mean([np.mean(res[ds][k]["idx"][:, 0] == np.asarray(tasks[ds]["files"][k]["targets"])) for k in res[ds]])) for ds in res}
+print(json.dumps({"workload": f"c5: {n_models} models x 10 tasks, {total} predictions, strings -> top-5 + paired score, 1 GPU",
+                  "seconds": dt, "predictions_per_s": total / dt, "files": n_models * len(TEST_ROWS),
+                  "class_sets": {ds: len(t["class_names"]) for ds, t in tasks.items()}, "top1_vs_random_targets": acc}))
+eng.close()
