@@ -79,6 +79,9 @@ struct EmbedArgs {
 // One warp per sequence; tokens visited in order so MPNet's position id (running count of
 // non-pad ids, modeling_mpnet.py:889-897) is a register counter. BERT: position = index
 // (modeling_bert.py:53-112, token_type 0 as the tokenizer emits for single sentences).
+// Two tokens are in flight per iteration (ids and positions first, then both gathers, both LayerNorms):
+// a token is a dependent chain gather -> reduce -> reduce -> store, and one chain per warp left the
+// kernel at 45 % of the HBM write roofline.
 template <int NV>
 __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
   const int lane = threadIdx.x & 31;
@@ -86,12 +89,14 @@ __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
   if (s >= a.n_seq) return;
   const int beg = a.cu[a.seq0 + s], end = a.cu[a.seq0 + s + 1];
   int running = 0;
-  for (int t = beg; t < end; ++t) {
-    int id = a.ids[t];
+  auto clamp_id = [&](int id) {
     if (id < 0 || id >= a.vocab) {
       if (lane == 0) atomicOr(a.status, 1);
       id = min(max(id, 0), a.vocab - 1);
     }
+    return id;
+  };
+  auto position = [&](int id, int t) {
     int p;
     if (a.mpnet) {
       const int np = (id != a.pad_id) ? 1 : 0;
@@ -100,10 +105,11 @@ __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
     } else {
       p = t - beg;
     }
-    p = min(p, a.max_pos - 1);
+    return min(p, a.max_pos - 1);
+  };
+  auto gather = [&](int id, int p, float4 (&x)[NV]) {
     const float4* w4 = reinterpret_cast<const float4*>(a.word + static_cast<size_t>(id) * a.H);
     const float4* p4 = reinterpret_cast<const float4*>(a.pos + static_cast<size_t>(p) * a.H);
-    float4 x[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
@@ -116,9 +122,27 @@ __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
         x[i] = make_float4(w.x + q.x, w.y + q.y, w.z + q.z, w.w + q.w);
       }
     }
+  };
+  auto store = [&](int t, float4 (&x)[NV]) {
     const size_t row = static_cast<size_t>(t - a.tok0);
-    ln_row_store<NV>(x, lane, a.H, a.gamma, a.beta, a.eps, a.x + row * a.H,
-                     a.xb ? a.xb + row * a.H : nullptr);
+    ln_row_store<NV>(x, lane, a.H, a.gamma, a.beta, a.eps, a.x + row * a.H, a.xb ? a.xb + row * a.H : nullptr);
+  };
+  int t = beg;
+  for (; t + 1 < end; t += 2) {
+    const int id0 = clamp_id(a.ids[t]), id1 = clamp_id(a.ids[t + 1]);
+    const int p0 = position(id0, t), p1 = position(id1, t + 1);
+    float4 x0[NV], x1[NV];
+    gather(id0, p0, x0);
+    gather(id1, p1, x1);
+    store(t, x0);
+    store(t + 1, x1);
+  }
+  if (t < end) {
+    const int id0 = clamp_id(a.ids[t]);
+    const int p0 = position(id0, t);
+    float4 x0[NV];
+    gather(id0, p0, x0);
+    store(t, x0);
   }
 }
 
