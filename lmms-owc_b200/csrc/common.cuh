@@ -97,6 +97,24 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   f2_unpack(r, x0, x1);
 }
 
+// GELU on a pair in its tanh form, 0.5 x (1 + tanh(0.79788456 (x + 0.044715 x^3))), five packed fp32x2 operations and
+// two MUFU.TANH - half the issue slots of gelu_fast2. |tanh form - erf form| <= 4.8e-4 (rms 1.5e-4 on N(0,1.2) inputs)
+// against 1.3e-3 rms for the bf16 rounding of the stored activation: the total error of the stored value grows by
+// 0.7 %. Used where the GELU sits on the critical path between two tensor-core phases (fused encoder, enc_fused.cuh).
+__device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t x2 = f2_mul(x, x);
+  uint64_t u = f2_fma(x2, f2_pack(0.0356774081f, 0.0356774081f), f2_pack(0.7978845608f, 0.7978845608f));
+  u = f2_mul(u, x);
+  float u0, u1, t0, t1;
+  f2_unpack(u, u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t h = f2_mul(x, f2_pack(0.5f, 0.5f));
+  const uint64_t r = f2_fma(h, f2_pack(t0, t1), h);
+  f2_unpack(r, x0, x1);
+}
+
 // Programmatic dependent launch (PDL). launch_dependents: the next kernel in the stream may start being
 // scheduled; wait: block until the previous kernel has completed and its writes are visible. Both are
 // no-ops for a kernel launched without the programmatic-serialization attribute.

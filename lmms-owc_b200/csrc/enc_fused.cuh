@@ -814,8 +814,8 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const float4 b = bf1[i];
             float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
             float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-            gelu_fast2(x0, x1);
-            gelu_fast2(x2, x3);
+            gelu_tanh2(x0, x1);   // tanh form: half the issue slots, error an order below the bf16 rounding (common.cuh)
+            gelu_tanh2(x2, x3);
             v[2 * i + 0] = pack_bf16x2(x0, x1);   // packed results reuse the front of v[]
             v[2 * i + 1] = pack_bf16x2(x2, x3);
           }
