@@ -602,8 +602,9 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
     LOAD_CU(cudaMemsetAsync(e->fx, 0, (static_cast<size_t>(e->fcap) + 128) * h * sizeof(float), c->stream));
     LOAD_CU(cudaMalloc(&e->fdbg, 2048 * sizeof(long long)));
     LOAD_CU(cudaMemsetAsync(e->fdbg, 0, 2048 * sizeof(long long), c->stream));
-    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
-    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
+    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
+    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
+    LOAD_CU(cudaFuncSetAttribute(k_encoder_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::SMEM_BYTES));
   }
   LOAD_CU(cudaStreamSynchronize(c->stream));  // `weights` may be freed by the caller after return
 #undef LOAD_CU
@@ -865,8 +866,9 @@ static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t*
       const int clusters = std::max(1, std::min(pairs, c->sm_count / 2));
       {
         ProfScope prof(c, OWC_KCAT_GEMM);
-        if (c->fused_dbg) k_encoder_fused<true><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
-        else k_encoder_fused<false><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
+        if (c->fused_dbg) k_encoder_fused<1><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
+        else if (fa.ablate) k_encoder_fused<2><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
+        else k_encoder_fused<0><<<2 * clusters, fz::THREADS, fz::SMEM_BYTES, c->stream>>>(e->tmf_qkv, e->tmf_o, e->tmf_1, e->tmf_2, fa);
       }
       OWC_TRY(check_launch(c, "k_encoder_fused"));
     }

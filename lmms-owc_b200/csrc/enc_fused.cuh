@@ -267,10 +267,14 @@ struct PhaseAcc {
   }
 };
 
-template <bool DBG>
+// MODE 0: production. MODE 1: phase accounting + event traces into a.dbg (tools/fused_check.py). MODE 2: role ablation
+// by a.ablate (tools/fused_ablate.py; wrong results by construction). The debug hooks compile away in MODE 0.
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fz::THREADS, 1)
 k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmWO,
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FusedArgs a) {
+  constexpr bool DBG = MODE == 1;
+  const int ablate = (MODE == 2) ? a.ablate : 0;
   using namespace fz;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -585,7 +589,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       pa.mark(6);
       pa.event(20);   // accx_full observed
       tc_fence_after();
-      if (a.ablate & 4) return;
+      if (ablate & 4) return;
       named_bar_sync(1, NSIMT * 32);   // the staged parameters (stage_ln_params) are visible to every warp
       uint64_t s2 = 0ull, q2 = 0ull;   // (0.f, 0.f)
       uint32_t v[32];
@@ -720,7 +724,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             pa.event(0);   // t1_full observed (attention)
             tc_fence_after();
             uint32_t v[CP];
-            if (!(a.ablate & 8)) {
+            if (!(ablate & 8)) {
               tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(gpart * CP), v);
             } else {
 #pragma unroll
@@ -754,7 +758,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             auto pre_store = [&]() {   // the O-projection of the previous head pair has read the AO tile
               if (!ao_ok) { mbar_wait(ao_free, (n_pair & 1) ^ 1); ao_ok = true; }
             };
-            for (int i = gw; i < ((a.ablate & 1) ? 0 : nseq); i += NSIMT / 2) {
+            for (int i = gw; i < ((ablate & 1) ? 0 : nseq); i += NSIMT / 2) {
               const int beg = seq_row[i];
               const int T = seq_row[i + 1] - beg;
               if (T <= 0) continue;
@@ -795,7 +799,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           pa.event(10);   // t1_full observed (FFN)
           tc_fence_after();
           uint32_t v[CP];
-          if (!(a.ablate & 8)) {
+          if (!(ablate & 8)) {
             tmem_ld_cols<CP>(tq + TM_T1 + static_cast<uint32_t>(part * CP), v);
           } else {
 #pragma unroll
@@ -808,7 +812,7 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           pa.mark(11);
           pa.event(11);   // drained
           const int fb = c & 1;
-          if (!(a.ablate & 2)) {
+          if (!(ablate & 2)) {
 #pragma unroll
           for (int i = 0; i < CP / 4; ++i) {
             const float4 b = bf1[i];
