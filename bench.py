@@ -88,6 +88,9 @@ class ClockSampler(threading.Thread):
 
 
 WORKLOADS = {
+    # configs[0]: the reference's own CPU-runnable case (for the record: `--workload c1`, 1000 rows unless --rows is given)
+    "c1": {"arch": "minilm-l6", "classes": "caltech101", "rows": 1000,
+           "desc": "c1: Caltech101 100 class names x 1k synthetic predictions, MiniLM-L6 arch, top-5 + paired score"},
     # BASELINE.json configs[1] - the headline single-GPU configuration
     "c2": {"arch": "minilm-l6", "classes": "food101", "desc": "c2: Food101 101 class names x 100k synthetic predictions per GPU, MiniLM-L6 arch, top-5 + paired score"},
     # configs[2]: ImageNet-1k-scale matching with the mpnet-base architecture (parity-tested; bench on request)
@@ -379,7 +382,7 @@ def run_ours(args) -> None:
                                  "peak": burst, "frac": tf / burst, "peak_source": f"{peak_src} bf16_tflops (kernel timed alone)",
                                  "algorithmic_bytes": 2 * h * (n_sim + c_sim) + 8 * 8 * n_sim}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_rate(2048, 2, 1, wl)
+        r = cpu_reference_rate(min(2048, rows), 2, 1, wl)
         line["cpu_baseline"] = {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"]}
     if rank == 0:
@@ -396,12 +399,14 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="prediction rows per GPU")
+    ap.add_argument("--rows", type=int, default=0, help="prediction rows per GPU (default: the workload's own size)")
     ap.add_argument("--chunk-tokens", type=int, default=0)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 is the headline; c3/c4 for the record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sim-leg", action="store_true")
     args = ap.parse_args()
+    if args.rows <= 0:
+        args.rows = WORKLOADS[args.workload].get("rows", ROWS_PER_GPU)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
