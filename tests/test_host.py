@@ -313,3 +313,36 @@ def test_sweep_groups_files_by_class_set(oracle_backed):
     assert np.abs(got["t1"]["m1"]["paired"] - b.gold["paired_scores"][40:100]).max() < 1e-5   # the reference's own scores
     with pytest.raises(ValueError):
         score_sweep(eng, tok, {"t": {"class_names": cls[:2], "files": {"m": {"predictions": ["x"], "targets": None}}}}, k=3)
+
+
+def test_eval_metrics_parallel_io_is_byte_identical(oracle_backed, tmp_path):
+    """N2: `--jobs` parses / rewrites files in worker processes (scoring stays here); files equal the serial path's
+    byte for byte, and `--skip-scored` leaves scored files alone."""
+    import shutil
+
+    import pandas as pd
+
+    from owc_b200 import eval_metrics as EM
+
+    b = oracle_backed
+    cls = [str(s) for s in b.gold["class_names"]]
+    preds = [str(s) for s in b.gold["preds"]]
+    tg = b.gold["targets"]
+    root = tmp_path / "logs"
+    for m in range(3):
+        run = root / "caltech101" / f"model-{m}"
+        run.mkdir(parents=True)
+        rows = [{"doc_id": i, "target": cls[tg[i]], "filtered_resps": [preds[i]], "note": "a/b é"} for i in range(20 * m, 20 * m + 30)]
+        pd.DataFrame(rows).to_json(run / "r_samples_caltech101.jsonl", lines=True, orient="records")
+    twin = tmp_path / "twin"
+    shutil.copytree(root, twin / "logs")
+    metrics = "semantic_similarity,mean_average_semantic_similarity"
+    serial = EM.main(EM.build_parser().parse_args(["-i", str(root), "-m", metrics]))
+    par = EM.main(EM.build_parser().parse_args(["-i", str(twin / "logs"), "-m", metrics, "--jobs", "2"]))
+    assert serial == par
+    for f in sorted(root.rglob("*.jsonl")):
+        g = twin / "logs" / f.relative_to(root)
+        assert f.read_bytes() == g.read_bytes()
+    before = {f: f.stat().st_mtime_ns for f in root.rglob("*.jsonl")}
+    again = EM.main(EM.build_parser().parse_args(["-i", str(root), "-m", metrics, "--skip-scored"]))
+    assert again == {} and before == {f: f.stat().st_mtime_ns for f in root.rglob("*.jsonl")}
