@@ -363,36 +363,50 @@ __global__ void __launch_bounds__(128) k_rescore(const float* __restrict__ zp, c
   int* ci = reinterpret_cast<int*>(cs + ncand);
   const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (r >= n) return;
-  const float* zr = zp + r * dim;
-  for (int c = 0; c < ncand; ++c) {
-    const int sp = c / KC, e = c % KC;
-    const int id = cand_idx[(static_cast<long long>(sp) * n + r) * KC + e];
-    float s = -INFINITY;
-    if (id >= 0) s = warp_dot(zr, zc + static_cast<long long>(id) * dim, dim, lane);
-    if (lane == 0) { cs[c] = s; ci[c] = id; }
+  // Four candidates at a time: 8 lanes per candidate, each lane a strided eighth of the row, three shuffles per dot
+  // (a whole warp per candidate spent 5 shuffles and a serialised store on every one of the 16 dots of a row).
+  const float4* zr4 = reinterpret_cast<const float4*>(zp + r * dim);
+  const int n4 = dim >> 2;                  // dim % 4 == 0 is checked by the callers
+  const int sub = lane & 7, grp = lane >> 3;
+  for (int c0 = 0; c0 < ncand; c0 += 4) {
+    const int c = c0 + grp;
+    int id = -1;
+    if (c < ncand) id = cand_idx[(static_cast<long long>(c / KC) * n + r) * KC + (c % KC)];
+    float acc = 0.f;
+    if (id >= 0) {
+      const float4* zc4 = reinterpret_cast<const float4*>(zc + static_cast<long long>(id) * dim);
+      for (int i = sub; i < n4; i += 8) {
+        const float4 x = zr4[i], y = __ldg(zc4 + i);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0 && c < ncand) { cs[c] = id >= 0 ? acc : -INFINITY; ci[c] = id; }
   }
   if (targets != nullptr && out_paired != nullptr) {
-    const float s = warp_dot(zr, zc + static_cast<long long>(targets[r]) * dim, dim, lane);
+    const float s = warp_dot(zp + r * dim, zc + static_cast<long long>(targets[r]) * dim, dim, lane);
     if (lane == 0) out_paired[r] = s;
   }
   __syncwarp();
-  if (lane == 0) {
-    for (int o = 0; o < k; ++o) {
-      int best = -1;
-      for (int c = 0; c < ncand; ++c) {
-        if (ci[c] < 0) continue;
-        if (best < 0 || better(cs[c], ci[c], cs[best], ci[best])) best = c;
-      }
-      if (best >= 0) {
-        out_scores[r * k + o] = cs[best];
-        out_idx[r * k + o] = ci[best];
-        ci[best] = -1;
-      } else {
-        out_scores[r * k + o] = -INFINITY;
-        out_idx[r * k + o] = -1;
-      }
+  // rank of every candidate among the valid ones under (score desc, index asc); ranks < k are the result rows
+  int n_valid = 0;
+  for (int c = lane; c < ncand; c += 32) {
+    const int id = ci[c];
+    if (id < 0) continue;
+    const float sc = cs[c];
+    int rank = 0;
+    for (int o = 0; o < ncand; ++o) {
+      const int oid = ci[o];
+      if (oid >= 0 && o != c && better(cs[o], oid, sc, id)) ++rank;
     }
+    if (rank < k) { out_scores[r * k + rank] = sc; out_idx[r * k + rank] = id; }
   }
+  for (int c = lane; c < ncand; c += 32) n_valid += ci[c] >= 0 ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+  for (int o = n_valid + lane; o < k; o += 32) { out_scores[r * k + o] = -INFINITY; out_idx[r * k + o] = -1; }
 }
 
 // Check mode: top-k of materialised fp32 score rows s[rows, C]. Warp per row; each lane keeps the
