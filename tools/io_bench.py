@@ -24,4 +24,16 @@ if __name__ == "__main__":
     with ProcessPoolExecutor(max_workers=16, mp_context=mp.get_context("spawn")) as pool:
         list(pool.map(EM._worker_load, files)); list(pool.map(EM._worker_write, [(f, cols) for f in files]))
     tp=time.perf_counter()-t
-    print(f"serial {ts:.2f}s  pool(16, incl. spawn) {tp:.2f}s for {len(files)} files of 8000 rows")
+    print(f"pandas: serial {ts:.2f}s  pool(16, incl. spawn) {tp:.2f}s for {len(files)} files of 8000 rows")
+    # native scanner (csrc/jsonl.cpp): serial, then 16 threads (the scanner runs outside the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    def native(f):
+        raw, items = EM._load_items_native(f)
+        EM._write_columns_native(f, raw, cols)
+    t=time.perf_counter()
+    for f in files: native(f)
+    tn=time.perf_counter()-t
+    t=time.perf_counter()
+    with ThreadPoolExecutor(16) as tp_: list(tp_.map(native, files))
+    tnt=time.perf_counter()-t
+    print(f"native: serial {tn:.2f}s  threads(16) {tnt:.2f}s")
