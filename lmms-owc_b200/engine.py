@@ -137,11 +137,18 @@ class Engine:
         return res
 
     def pair_dot(self, a, b, a_index=None, b_index=None) -> np.ndarray:
-        """``out[i] = <a[a_index[i]], b[b_index[i]]>`` (identity index when ``None``) on host arrays.
+        """``out[i] = <a[a_index[i]], b[b_index[i]]>`` (identity index when ``None``), fp32 numpy ``[n]``.
 
-        ``owc_pair_dot``; reference: the ``torch.bmm`` at ``_group.py:541-544``."""
-        a = np.ascontiguousarray(a, dtype=np.float32)
-        b = np.ascontiguousarray(b, dtype=np.float32)
+        ``a`` / ``b`` are host arrays, or both CUDA tensors straight from ``encode(..., out='device')`` - then only the
+        index vectors go up and the ``n`` scores come down. ``owc_pair_dot``; reference: the ``torch.bmm`` at
+        ``_group.py:541-544``."""
+        torch = _torch()
+        on_dev = isinstance(a, torch.Tensor) and a.is_cuda
+        if on_dev != (isinstance(b, torch.Tensor) and b.is_cuda):
+            raise ValueError("pair_dot: a and b must live in the same memory space")
+        if not on_dev:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
         if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
             raise ValueError("pair_dot needs [na, dim] and [nb, dim] arrays")
         ai = None if a_index is None else np.ascontiguousarray(a_index, dtype=np.int32)
@@ -153,12 +160,26 @@ class Engine:
             raise IndexError("a_index out of range")
         if bi is not None and n and (bi.min() < 0 or bi.max() >= b.shape[0]):
             raise IndexError("b_index out of range")
-        out = np.empty(n, dtype=np.float32)
-        if n:
+        if not n:
+            return np.empty(0, dtype=np.float32)
+        if on_dev:
+            p_a, _, keep_a = _as_arg(a, np.float32, self.device)
+            p_b, _, keep_b = _as_arg(b, np.float32, self.device)
+            dev = self.torch_device
+            ai_d = None if ai is None else torch.from_numpy(ai).to(dev)
+            bi_d = None if bi is None else torch.from_numpy(bi).to(dev)
+            out_d = torch.empty(n, dtype=torch.float32, device=dev)
+            self._enter()
             _cabi.check(self._lib.owc_pair_dot(
-                self._ctx, a.ctypes.data, a.shape[0], ai.ctypes.data if ai is not None else None, b.ctypes.data,
-                b.shape[0], bi.ctypes.data if bi is not None else None, n, a.shape[1], _cabi.MEM_HOST,
-                out.ctypes.data))
+                self._ctx, p_a, keep_a.shape[0], ai_d.data_ptr() if ai_d is not None else None, p_b, keep_b.shape[0],
+                bi_d.data_ptr() if bi_d is not None else None, n, keep_a.shape[1], _cabi.MEM_DEVICE, out_d.data_ptr()))
+            self._leave()
+            return out_d.cpu().numpy()
+        out = np.empty(n, dtype=np.float32)
+        _cabi.check(self._lib.owc_pair_dot(
+            self._ctx, a.ctypes.data, a.shape[0], ai.ctypes.data if ai is not None else None, b.ctypes.data,
+            b.shape[0], bi.ctypes.data if bi is not None else None, n, a.shape[1], _cabi.MEM_HOST,
+            out.ctypes.data))
         return out
 
     def sim_topk(self, zp, zc, k: int, precision: str | None = None):

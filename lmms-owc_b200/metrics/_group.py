@@ -38,8 +38,9 @@ def _select(items: list) -> tuple[list[str], list[str]]:
 def _paired_scores(refs: list[str], preds: list[str]) -> np.ndarray:
     """``s_i = <z(ref_i), z(pred_i)>`` (the ``torch.bmm`` of _group.py:537-544), fp32 [N]."""
     engine, _ = _text.get_engine()
-    zr, ridx = _text.encode_unique(refs)
-    zp, pidx = _text.encode_unique(preds)
+    # embeddings stay in device memory between the two calls: only token ids / indices go up and N scores come down
+    zr, ridx = _text.encode_unique(refs, out="device")
+    zp, pidx = _text.encode_unique(preds, out="device")
     return engine.pair_dot(zr, zp, a_index=ridx, b_index=pidx)
 
 

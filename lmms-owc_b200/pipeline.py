@@ -18,10 +18,14 @@ __all__ = ["score_strings_pipelined"]
 
 
 def score_strings_pipelined(engine, tokenizer, predictions: list[str], zc_device, targets=None, k: int = 1,
-                            chunk_rows: int = 20_000, precision: str | None = None) -> dict:
+                            chunk_rows: int = 20_000, precision: str | None = None,
+                            first_chunk_rows: int | None = None) -> dict:
     """Tokenise + encode + match ``predictions`` against class embeddings ``zc_device`` (CUDA fp32 ``[C, H]``).
 
-    Returns numpy ``{"scores" [n,k], "idx" [n,k], "paired" [n] or None}`` in the original row order.
+    ``first_chunk_rows`` (default: ``chunk_rows``) sizes the first chunk separately: its tokenisation is the only one
+    the device has to wait for, so a short first chunk followed by long ones starts the device early and keeps the
+    per-chunk launch overhead low. Returns numpy ``{"scores" [n,k], "idx" [n,k], "paired" [n] or None}`` in the
+    original row order.
     """
     if not isinstance(predictions, list):
         raise NotImplementedError
@@ -34,7 +38,8 @@ def score_strings_pipelined(engine, tokenizer, predictions: list[str], zc_device
     if n == 0:
         return out
     chunk_rows = max(1, int(chunk_rows))
-    bounds = [(lo, min(lo + chunk_rows, n)) for lo in range(0, n, chunk_rows)]
+    first = min(n, chunk_rows if first_chunk_rows is None else max(1, int(first_chunk_rows)))
+    bounds = [(0, first)] + [(lo, min(lo + chunk_rows, n)) for lo in range(first, n, chunk_rows)]
     ready: queue.Queue = queue.Queue(maxsize=2)   # at most two tokenised chunks ahead of the device
 
     def producer() -> None:

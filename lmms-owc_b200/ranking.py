@@ -38,7 +38,7 @@ def semantic_similarity_game_scores(matches: list[dict], threshold: float = WIN_
     texts = ([m["reference"] for m in matches] + [m["player_a_response"] for m in matches]
              + [m["player_b_response"] for m in matches])
     engine, _ = _text.get_engine()
-    z, inv = _text.encode_unique(texts)          # one table for all three columns
+    z, inv = _text.encode_unique(texts, out="device")          # one table for all three columns, kept on the device
     ref_i, a_i, b_i = inv[:n], inv[n:2 * n], inv[2 * n:]
     sim_a = np.asarray(engine.pair_dot(z, z, a_index=ref_i, b_index=a_i), dtype=np.float32)
     sim_b = np.asarray(engine.pair_dot(z, z, a_index=ref_i, b_index=b_i), dtype=np.float32)

@@ -75,6 +75,13 @@ def test_pair_dot_with_and_without_index(tiny_engine):
     assert tiny_engine.pair_dot(a[:0], b[:0]).shape == (0,)
     with pytest.raises(IndexError):
         tiny_engine.pair_dot(a, b, a_index=np.full(1000, 37, np.int32))
+    # device-resident tables (what the metric bodies pass): bit-identical to the host-buffer call
+    ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    assert np.array_equal(tiny_engine.pair_dot(ad, bd, a_index=ai), tiny_engine.pair_dot(a, b, a_index=ai))
+    assert np.array_equal(tiny_engine.pair_dot(bd, bd), tiny_engine.pair_dot(b, b))
+    assert np.array_equal(tiny_engine.pair_dot(ad, bd, a_index=ai[:5], b_index=bi), tiny_engine.pair_dot(a, b, a_index=ai[:5], b_index=bi))
+    with pytest.raises(ValueError):
+        tiny_engine.pair_dot(ad, b, a_index=ai)
 
 
 def _unit_rows(n, d, seed, spread=0.3):
