@@ -9,6 +9,9 @@ exactly like the reference's registry lookup. Differences, all additive:
 
 * the sample file is rewritten atomically (temp file + ``os.replace``) instead of in place;
 * ``--jobs N`` parses / rewrites files in N workers, ``--skip-scored`` skips files that already carry the columns;
+* launched under ``torchrun`` (``WORLD_SIZE`` > 1) the files are dealt out to the ranks by size, every rank scores its
+  own files on its own GPU (the reference spreads ``datasets.map`` over the GPUs with ``num_proc``, ``_group.py:521-535``)
+  and rank 0 prints the report;
 * ``--io native`` reads and rewrites the files with the library's streaming JSONL scanner (``jsonl.py``) instead of
   pandas: same records, untouched members keep their bytes, ~8x less host time per file.
 
@@ -233,6 +236,35 @@ def score_files(input_files: list[str], metric_names: list[str], jobs: int = 1, 
     return results
 
 
+# ---- one process per GPU: files are independent units, so ranks share nothing but the final report -----------------
+def split_files_balanced(input_files: list[str], world: int) -> list[list[str]]:
+    """Deal files to ``world`` ranks, largest first onto the lightest rank (bytes on disk stand in for rows); every
+    rank computes the same deal from the same sorted list. Order inside a rank follows ``input_files``."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    sizes = {f: (os.path.getsize(f) if os.path.exists(f) else 0) for f in input_files}
+    load = [0] * world
+    owner = {}
+    for f in sorted(input_files, key=lambda f: (-sizes[f], f)):
+        r = min(range(world), key=lambda i: (load[i], i))
+        owner[f] = r
+        load[r] += sizes[f] + 1
+    return [[f for f in input_files if owner[f] == r] for r in range(world)]
+
+
+def _dist_context():
+    """``(rank, world, local_rank)`` from the launcher's environment (torchrun); initialises a gloo group for the one
+    object gather the CLI needs (results are a few floats per file; the data path has no collective)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, 0
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")
+    return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+
+
 def format_report(tasks_outputs: dict) -> str:
     """``eval_metrics.py:155-171``: one block per (task, metric), one ``{model:<29}: {value:.3f}`` line per model."""
     blocks = []
@@ -260,8 +292,24 @@ def main(args: Namespace) -> dict:
     input_files = find_input_files(args.input)
     log.info("Found %d `jsonl` files to process", len(input_files))
     tasks_outputs: dict = {}
-    per_file = score_files(input_files, args.metrics.split(","), jobs=getattr(args, "jobs", 1),
+    rank, world, local_rank = _dist_context()
+    mine = input_files
+    if world > 1:
+        from . import text as _text
+
+        _text.default_rank = local_rank
+        mine = split_files_balanced(input_files, world)[rank]
+        log.info("Rank %d/%d scores %d of the files", rank, world, len(mine))
+    per_file = score_files(mine, args.metrics.split(","), jobs=getattr(args, "jobs", 1),
                            skip_scored=getattr(args, "skip_scored", False), io=getattr(args, "io", "pandas"))
+    if world > 1:
+        import torch.distributed as dist
+
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(per_file, parts, dst=0)
+        if rank != 0:
+            return {}
+        per_file = {f: out for part in parts for f, out in part.items()}
     for input_file in input_files:
         if input_file not in per_file:
             continue

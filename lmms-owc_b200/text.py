@@ -23,6 +23,7 @@ MODEL_NAME = "sentence-transformers/all-MiniLM-L6-v2"  # _text.py:161
 sentence_bert_model: Engine | None = None          # same global names as the reference module
 sentence_bert_processor: HostTokenizer | None = None
 concept_extractor = None                           # callable(batch, **kwargs) -> batch; default spaCy
+default_rank: int | None = None                    # GPU chosen when a caller passes rank=None (set by multi-process CLIs)
 
 
 def configure(arch: _arch.EncoderArch, state_dict: dict, vocab: list[str], device: int | None = None,
@@ -63,7 +64,7 @@ def _lazy_load(rank: int | None) -> None:
 
 def get_engine(rank: int | None = None) -> tuple[Engine, HostTokenizer]:
     if sentence_bert_model is None:
-        _lazy_load(rank)
+        _lazy_load(default_rank if rank is None else rank)
     return sentence_bert_model, sentence_bert_processor
 
 

@@ -139,3 +139,91 @@ def test_sharded_scoring_world2_matches_single_process():
     # rank 0 encodes the class names (1) + its rows (1); rank 1 only probes + encodes its rows: the
     # class embeddings reach it by broadcast, not by re-encoding
     assert r0["calls"] == 2 and r1["calls"] == 2
+
+
+# ---- the CLI mirror under a multi-process launcher: files dealt to ranks, one report on rank 0 -------------------
+class _PairEngine(_OracleEngine):
+    """Adds the paired dot the metric bodies call."""
+
+    def pair_dot(self, a, b, a_index=None, b_index=None):
+        a, b = torch.as_tensor(a), torch.as_tensor(b)
+        if a_index is not None:
+            a = a[torch.from_numpy(np.asarray(a_index)).long()]
+        if b_index is not None:
+            b = b[torch.from_numpy(np.asarray(b_index)).long()]
+        return (a * b).sum(1).numpy()
+
+    def close(self):
+        pass
+
+
+def _write_cli_logs(root, classes, preds, targets):
+    import json
+
+    sizes = [25, 9, 17, 10]                                    # different sizes: the deal is by bytes on disk
+    lo = 0
+    for m, n in enumerate(sizes):
+        run = os.path.join(root, "task", f"model-{m}")
+        os.makedirs(run)
+        with open(os.path.join(run, "r_samples_task.jsonl"), "w", encoding="utf-8") as f:
+            for i in range(lo, lo + n):
+                f.write(json.dumps({"doc_id": i, "target": classes[targets[i]], "filtered_resps": [preds[i]]}) + "\n")
+        lo += n
+
+
+def _cli_worker(rank, world, port, root, queue):
+    sys.path.insert(0, ROOT)
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank)})
+    torch.set_num_threads(1)
+    from owc_b200 import eval_metrics as EM
+    from owc_b200 import text as T
+
+    arch, sd, tok, *_ = _small_setup()
+    T.sentence_bert_model, T.sentence_bert_processor = _PairEngine(arch, sd), tok
+    try:
+        out = EM.main(EM.build_parser().parse_args(["-i", root, "-m", "semantic_similarity", "--io", "native",
+                                                    "--log-level", "WARNING"]))
+        queue.put({"rank": rank, "out": out, "default_rank": T.default_rank})
+    finally:
+        T.sentence_bert_model = T.sentence_bert_processor = None
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_cli_deals_files_to_ranks_world2(tmp_path, monkeypatch):
+    import shutil
+
+    from owc_b200 import eval_metrics as EM
+    from owc_b200 import text as T
+
+    arch, sd, tok, classes, preds, targets = _small_setup()
+    one, two = str(tmp_path / "one" / "logs"), str(tmp_path / "two" / "logs")
+    _write_cli_logs(one, classes, preds, targets)
+    shutil.copytree(one, two)
+    files = EM.find_input_files(two)
+    deal = EM.split_files_balanced(files, 2)
+    assert sorted(deal[0] + deal[1]) == files and all(deal) and EM.split_files_balanced(files, 1) == [files]
+    loads = [sum(os.path.getsize(f) for f in part) for part in deal]
+    assert abs(loads[0] - loads[1]) <= max(os.path.getsize(f) for f in files)
+    assert EM.split_files_balanced(files, 2) == deal and len(EM.split_files_balanced(files[:1], 3)) == 3
+
+    monkeypatch.setattr(T, "sentence_bert_model", _PairEngine(arch, sd))
+    monkeypatch.setattr(T, "sentence_bert_processor", tok)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    single = EM.main(EM.build_parser().parse_args(["-i", one, "-m", "semantic_similarity", "--io", "native",
+                                                   "--log-level", "WARNING"]))
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cli_worker, args=(r, 2, port, two, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {r["rank"]: r for r in (queue.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0]["out"] == single and results[1]["out"] == {}            # one report, on rank 0
+    assert results[0]["default_rank"] == 0 and results[1]["default_rank"] == 1  # each rank on its own GPU
+    for f in EM.find_input_files(one):
+        assert open(f, "rb").read() == open(f.replace(one, two), "rb").read()  # every file scored exactly once
