@@ -195,8 +195,9 @@ int32_t owc_tokenize_packed(const owc_tokenizer* tok, const char* text_bytes, co
 #define OWC_JSONL_ERROR 1
 #define OWC_JSONL_UNSUPPORTED 2
 #define OWC_JSONL_FIRST 0 /* "s" -> s, ["s0", ...] -> s0: the reference string, `ref[0]` of _group.py:518          */
-#define OWC_JSONL_LAST 1  /* "s" -> s, [..., "sn"] -> sn, [[..., "sn"], ...] -> sn of the first inner list: the
-                             scored prediction, eval_metrics.py:66-68 followed by `pred[-1]` of _group.py:519       */
+#define OWC_JSONL_LAST 1  /* the scored prediction: `pred[-1]` of _group.py:519 ("s" -> s, [..., "sn"] -> sn) applied
+                             to the row's value, or to its FIRST element when the file is multi-round, which
+                             eval_metrics.py:66-68 decides once per file on the first row ([[...], ...])            */
 #define OWC_JSONL_FLOAT 0 /* written as pandas writes doubles: "%.10f", trailing zeros trimmed, NaN/inf -> null    */
 #define OWC_JSONL_INT 1
 const char* owc_jsonl_last_error(void);

@@ -218,55 +218,70 @@ void for_lines(const char* buf, size_t len, F&& f) {
     }
 }
 
-// The string the similarity metrics take from one member value:
-//   mode FIRST (references, `_group.py:518`): "s" -> s ; ["s0", ...] -> s0
-//   mode LAST  (predictions, `eval_metrics.py:66-68` then `_group.py:519`): "s" -> s ; [.., "sn"] -> sn ;
-//              [[.., "sn"], ...] -> sn of the FIRST inner list (multi-round responses)
-// Returns the span of that string, or nullptr when the value has another shape (the caller then falls back).
-bool pick_string(const char* b, const char* e, int mode, size_t line, const char** sb, const char** se, int depth = 0) {
-    if (b >= e) return false;
-    if (*b == '"') {
-        *sb = b;
-        *se = skip_string(b, e, line);
-        return true;
-    }
-    if (*b != '[') return false;
+// First and last element of the JSON list [b, e); false when the value is not a list or the list is empty.
+struct ListEnds {
+    const char* first_b;
+    const char* first_e;
+    const char* last_b;
+    const char* last_e;
+};
+
+bool list_ends(const char* b, const char* e, size_t line, ListEnds* out) {
+    if (b >= e || *b != '[') return false;
     const char* p = skip_ws(b + 1, e);
-    if (p < e && *p == ']') return false;                      // empty list: the reference raises IndexError
-    const char* first_b = nullptr;
-    const char* first_e = nullptr;
-    const char* last_b = nullptr;
-    const char* last_e = nullptr;
+    if (p < e && *p == ']') return false;
+    out->first_b = nullptr;
     for (;;) {
         p = skip_ws(p, e);
         const char* vb = p;
         const char* ve = skip_value(p, e, line);
-        if (!first_b) {
-            first_b = vb;
-            first_e = ve;
+        if (!out->first_b) {
+            out->first_b = vb;
+            out->first_e = ve;
         }
-        last_b = vb;
-        last_e = ve;
+        out->last_b = vb;
+        out->last_e = ve;
         p = skip_ws(ve, e);
         if (p >= e) fail(line, "unterminated list");
-        if (*p == ']') break;
+        if (*p == ']') return true;
         if (*p != ',') fail(line, "',' or ']' expected");
         ++p;
     }
-    if (mode == OWC_JSONL_FIRST) {
-        if (*first_b != '"') return false;
-        *sb = first_b;
-        *se = first_e;
-        return true;
-    }
-    if (*first_b == '[') {                                      // multi-round: inner list of the first round
-        if (depth > 0) return false;
-        return pick_string(first_b, first_e, mode, line, sb, se, depth + 1);
-    }
-    if (*last_b != '"') return false;
-    *sb = last_b;
-    *se = last_e;
+}
+
+inline bool take_string(const char* b, const char* e, size_t line, const char** sb, const char** se) {
+    if (b >= e || *b != '"') return false;
+    *sb = b;
+    *se = skip_string(b, e, line);
     return true;
+}
+
+// The reference string of a row (`ref[0] if isinstance(ref, list) else ref`, `_group.py:518`):
+//   "s" -> s ; ["s0", ...] -> s0. False for any other shape (the caller then reports the file as unsupported).
+bool pick_reference(const char* b, const char* e, size_t line, const char** sb, const char** se) {
+    if (take_string(b, e, line, sb, se)) return true;
+    ListEnds le;
+    return list_ends(b, e, line, &le) && take_string(le.first_b, le.first_e, line, sb, se);
+}
+
+// `eval_metrics.py:66-68` decides ONCE per file, on the first row, whether the responses are multi-round
+// (`predictions[0][0]` is a list) and then takes `prediction[0]` of every row.
+bool is_multi_round(const char* b, const char* e, size_t line) {
+    ListEnds le;
+    return list_ends(b, e, line, &le) && *le.first_b == '[';
+}
+
+// The scored prediction of a row (`pred[-1] if isinstance(pred, list) else pred`, `_group.py:519`, applied to the
+// row's value, or to its first element in a multi-round file): the result must be a string.
+bool pick_prediction(const char* b, const char* e, bool multi_round, size_t line, const char** sb, const char** se) {
+    ListEnds le;
+    if (multi_round) {                                          // pred = value[0]
+        if (!list_ends(b, e, line, &le)) return false;          // (a bare string would be indexed by character)
+        b = le.first_b;
+        e = le.first_e;
+    }
+    if (take_string(b, e, line, sb, se)) return true;
+    return list_ends(b, e, line, &le) && take_string(le.last_b, le.last_e, line, sb, se);
 }
 
 // pandas' ujson writer: fixed notation, 10 decimals, trailing zeros trimmed to one, NaN / inf -> null.
@@ -320,6 +335,7 @@ int owc_jsonl_extract(const char* buf, size_t len, const char* key, int mode, ch
         std::string blob;
         blob.reserve(len / 8 + 64);
         bool fallback = false;
+        bool multi_round = false;
         size_t rows = 0;
         for_lines(buf, len, [&](const char* a, const char* b, size_t line) {
             if (fallback) return;
@@ -333,7 +349,10 @@ int owc_jsonl_extract(const char* buf, size_t len, const char* key, int mode, ch
             });
             const char* sb;
             const char* se;
-            if (!vb || !pick_string(vb, ve, mode, line, &sb, &se) || !decode_string(sb, se, blob, line)) {
+            if (vb && mode == OWC_JSONL_LAST && rows == 0) multi_round = is_multi_round(vb, ve, line);
+            const bool ok = vb && (mode == OWC_JSONL_FIRST ? pick_reference(vb, ve, line, &sb, &se)
+                                                           : pick_prediction(vb, ve, multi_round, line, &sb, &se));
+            if (!ok || !decode_string(sb, se, blob, line)) {
                 fallback = true;
                 return;
             }

@@ -57,12 +57,24 @@ def test_reader_matches_pandas_selection(ascii_only, sep):
 def test_reader_multi_round_and_list_targets():
     from owc_b200 import jsonl
 
-    rows = [{"target": ["cat", "feline"], "filtered_resps": [["round one", "a cat"], ["round two"]]},
-            {"target": "dog", "filtered_resps": [["only"]]},
-            {"filtered_resps": "bare string", "target": "x", "filtered_resps_extra": ["no"]},
-            {"target": "dup", "filtered_resps": ["old"], "pad": 1, "filtered_resps ": ["key with space"]}]
-    raw = ("\n".join(json.dumps(r) for r in rows)).encode()            # no trailing newline
-    assert jsonl.read_pairs(raw) == [("cat", "a cat"), ("dog", "only"), ("x", "bare string"), ("dup", "old")]
+    def dump(rows):
+        return ("\n".join(json.dumps(r) for r in rows)).encode()            # no trailing newline
+
+    # multi-round is decided once per file, on the first row (eval_metrics.py:66-68), then `prediction[0]` for all
+    multi = [{"target": ["cat", "feline"], "filtered_resps": [["round one", "a cat"], ["round two"]]},
+             {"target": "dog", "filtered_resps": [["only"]]},
+             {"target": "cow", "filtered_resps": ["flat in a multi-round file", "ignored"]}]
+    assert jsonl.read_pairs(dump(multi)) == _expected_pairs(dump(multi))[0] == [
+        ("cat", "a cat"), ("dog", "only"), ("cow", "flat in a multi-round file")]
+    flat = [{"filtered_resps": "bare string", "target": "x", "filtered_resps_extra": ["no"]},
+            {"target": "dup", "filtered_resps": ["old"], "pad": 1, "filtered_resps ": ["key with space"]},
+            {"target": "mix", "filtered_resps": [["nested but not first row"], "last wins"]}]
+    assert jsonl.read_pairs(dump(flat)) == _expected_pairs(dump(flat))[0] == [
+        ("x", "bare string"), ("dup", "old"), ("mix", "last wins")]
+    with pytest.raises(jsonl.Unsupported):                 # the reference would hand a list to the tokenizer
+        jsonl.read_pairs(dump(flat + [{"target": "t", "filtered_resps": [["a", "b"]]}]))
+    with pytest.raises(jsonl.Unsupported):                 # ... or index a string by character
+        jsonl.read_pairs(dump(multi + [{"target": "t", "filtered_resps": "bare"}]))
     # a repeated member: the last one wins, as in json.loads
     assert jsonl.read_pairs(b'{"target":"a","filtered_resps":["p"],"target":"b"}') == [("b", "p")]
     assert jsonl.read_pairs(b"") == [] and jsonl.read_pairs(b"\n \n") == []
@@ -212,8 +224,13 @@ def test_fuzz_against_json():
         seps = rnd.choice([(",", ":"), (", ", ": "), (" ,  ", " :\t")])
         lines.append(" " * rnd.randrange(3) + json.dumps(rec, ensure_ascii=bool(i % 2), separators=seps) + " " * rnd.randrange(3))
     raw = "\n".join(lines).encode()
-    exp = [((r["target"][0] if isinstance(r["target"], list) else r["target"]),
-            (r["filtered_resps"][0][-1] if isinstance(r["filtered_resps"][0], list) else r["filtered_resps"][-1])) for r in recs]
+    multi = isinstance(recs[0]["filtered_resps"][0], list)             # decided on the first row, applied to all
+    exp = []
+    for r in recs:
+        pred = r["filtered_resps"][0] if multi else r["filtered_resps"]
+        exp.append((r["target"][0] if isinstance(r["target"], list) else r["target"],
+                    pred[-1] if isinstance(pred, list) else pred))
+    assert multi
     assert jsonl.read_pairs(raw) == exp
     vals = [rnd.uniform(-1, 1) for _ in recs]
     out = jsonl.render_columns(raw, {"score": vals, "hit": [int(v > 0) for v in vals]})
