@@ -206,6 +206,11 @@ int32_t owc_jsonl_count_rows(const char* buf, size_t len, size_t* n_rows);
  * out (out_cap >= len always suffices). Rows are in file order; *n_rows = rows written.                           */
 int32_t owc_jsonl_extract(const char* buf, size_t len, const char* key, int32_t mode, char* out, size_t out_cap,
                           size_t* out_len, size_t* n_rows);
+/* Both strings of every row in ONE pass: ref_key with OWC_JSONL_FIRST into out_refs, pred_key with OWC_JSONL_LAST into
+ * out_preds (each cap >= len always suffices); what the CLI uses with ("target", "filtered_resps").              */
+int32_t owc_jsonl_extract_pairs(const char* buf, size_t len, const char* ref_key, const char* pred_key, char* out_refs,
+                                size_t refs_cap, size_t* refs_len, char* out_preds, size_t preds_cap,
+                                size_t* preds_len, size_t* n_rows);
 /* *all_rows = 1 iff the buffer has at least one row and every row carries every member of names[].               */
 int32_t owc_jsonl_has_members(const char* buf, size_t len, const char* const* names, int32_t n_names,
                               int32_t* all_rows);
@@ -214,6 +219,10 @@ int32_t owc_jsonl_has_members(const char* buf, size_t len, const char* const* na
 int32_t owc_jsonl_set_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
                               const double* values, int32_t n_cols, size_t n_rows, char* out, size_t out_cap,
                               size_t* out_len);
+/* The same text written straight to the file out_path (created / truncated; removed again on failure): the caller
+ * renames it over the samples file, so a crash never leaves a truncated one.                                      */
+int32_t owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                                const double* values, int32_t n_cols, size_t n_rows, const char* out_path);
 
 /* Debug: timeline of the block-resident fused encoder kernel (enc_fused.cuh). When the ctx was created with
  * OWC_FUSED_DBG=1 in the environment, the first SIMT thread of CTA 0 records clock64 at: block start,

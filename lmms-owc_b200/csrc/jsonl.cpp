@@ -300,6 +300,61 @@ inline void put_double(std::string& out, double v) {
     out.append(tmp, (size_t)n);
 }
 
+// Copies every row with its other members byte for byte, drops members named in names[] and appends
+// names[i]:values[i * n_rows + row]; hands the text to `sink` whenever `flush_at` bytes have accumulated and at the end.
+template <class Sink>
+void render_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds, const double* values,
+                    int n_cols, size_t n_rows, size_t flush_at, Sink&& sink) {
+    std::vector<size_t> nl((size_t)n_cols);
+    for (int i = 0; i < n_cols; ++i) nl[(size_t)i] = strlen(names[i]);
+    std::string dst;
+    dst.reserve(flush_at == ~size_t(0) ? len + n_rows * 32 * (size_t)(n_cols + 1) : flush_at + (size_t(1) << 16));
+    size_t rows = 0;
+    for_lines(buf, len, [&](const char* a, const char* b, size_t line) {
+        if (rows >= n_rows) fail(line, "more rows than values");
+        dst.push_back('{');
+        bool any = false;
+        // kept members are copied with the source's own spacing and separators, as few runs as possible: a run ends
+        // where a member is dropped (a row scored for the first time is one memcpy)
+        const char* run_b = nullptr;
+        const char* run_e = nullptr;
+        walk_members(a, b, line, [&](const Member& m, const char* k, size_t kl) {
+            for (int i = 0; i < n_cols; ++i)
+                if (kl == nl[(size_t)i] && memcmp(k, names[i], kl) == 0) {
+                    if (run_b) dst.append(run_b, (size_t)(run_e - run_b));
+                    run_b = nullptr;
+                    return;
+                }
+            if (!run_b) {
+                if (any) dst.push_back(',');
+                run_b = m.lead_b;
+            }
+            run_e = m.val_e;
+            any = true;
+        });
+        if (run_b) dst.append(run_b, (size_t)(run_e - run_b));
+        for (int i = 0; i < n_cols; ++i) {
+            if (any) dst.push_back(',');
+            dst.push_back('"');
+            dst.append(names[i], nl[(size_t)i]);
+            dst += "\":";
+            const double v = values[(size_t)i * n_rows + rows];
+            if (kinds[i] == OWC_JSONL_INT && std::isfinite(v)) dst += std::to_string((long long)v);
+            else put_double(dst, v);
+            any = true;
+        }
+        dst += "}\n";
+        ++rows;
+        if (dst.size() >= flush_at) {
+            sink(dst);
+            dst.clear();
+        }
+    });
+    if (rows != n_rows) throw Fail{"jsonl: " + std::to_string(rows) + " rows in the file, " + std::to_string(n_rows) +
+                                   " values per column"};
+    if (!dst.empty()) sink(dst);
+}
+
 template <class F>
 int guarded(F&& f) {
     try {
@@ -371,6 +426,56 @@ int owc_jsonl_extract(const char* buf, size_t len, const char* key, int mode, ch
     });
 }
 
+int owc_jsonl_extract_pairs(const char* buf, size_t len, const char* ref_key, const char* pred_key, char* out_refs,
+                            size_t refs_cap, size_t* refs_len, char* out_preds, size_t preds_cap, size_t* preds_len,
+                            size_t* n_rows) {
+    return guarded([&] {
+        const size_t rl = strlen(ref_key), pl = strlen(pred_key);
+        std::string refs, preds;
+        refs.reserve(len / 16 + 64);
+        preds.reserve(len / 8 + 64);
+        bool fallback = false;
+        bool multi_round = false;
+        size_t rows = 0;
+        for_lines(buf, len, [&](const char* a, const char* b, size_t line) {
+            if (fallback) return;
+            const char *rb = nullptr, *re = nullptr, *pb = nullptr, *pe = nullptr;
+            walk_members(a, b, line, [&](const Member& m, const char* k, size_t kl) {
+                if (kl == rl && memcmp(k, ref_key, rl) == 0) {         // duplicates: the last one wins, like json.loads
+                    rb = m.val_b;
+                    re = m.val_e;
+                } else if (kl == pl && memcmp(k, pred_key, pl) == 0) {
+                    pb = m.val_b;
+                    pe = m.val_e;
+                }
+            });
+            const char* sb;
+            const char* se;
+            if (pb && rows == 0) multi_round = is_multi_round(pb, pe, line);
+            if (!rb || !pb || !pick_reference(rb, re, line, &sb, &se) || !decode_string(sb, se, refs, line) ||
+                !pick_prediction(pb, pe, multi_round, line, &sb, &se) || !decode_string(sb, se, preds, line)) {
+                fallback = true;
+                return;
+            }
+            refs.push_back('\0');
+            preds.push_back('\0');
+            ++rows;
+        });
+        if (fallback) {
+            g_jsonl_err = std::string("jsonl: member '") + ref_key + "' or '" + pred_key +
+                          "' is missing or has a shape the fast path does not cover";
+            return OWC_JSONL_UNSUPPORTED;
+        }
+        if (refs.size() > refs_cap || preds.size() > preds_cap) throw Fail{"jsonl: output buffer too small"};
+        memcpy(out_refs, refs.data(), refs.size());
+        memcpy(out_preds, preds.data(), preds.size());
+        *refs_len = refs.size();
+        *preds_len = preds.size();
+        *n_rows = rows;
+        return OWC_JSONL_OK;
+    });
+}
+
 int owc_jsonl_has_members(const char* buf, size_t len, const char* const* names, int n_names, int* all_rows) {
     return guarded([&] {
         std::vector<size_t> nl((size_t)n_names);
@@ -397,41 +502,36 @@ int owc_jsonl_set_columns(const char* buf, size_t len, const char* const* names,
                           const double* values, int n_cols, size_t n_rows, char* out, size_t out_cap,
                           size_t* out_len) {
     return guarded([&] {
-        std::vector<size_t> nl((size_t)n_cols);
-        for (int i = 0; i < n_cols; ++i) nl[(size_t)i] = strlen(names[i]);
-        std::string dst;
-        dst.reserve(len + n_rows * 32 * (size_t)(n_cols + 1));
-        size_t rows = 0;
-        for_lines(buf, len, [&](const char* a, const char* b, size_t line) {
-            if (rows >= n_rows) fail(line, "more rows than values");
-            // copy the members that are not being (re)written, verbatim
-            dst.push_back('{');
-            bool any = false;
-            walk_members(a, b, line, [&](const Member& m, const char* k, size_t kl) {
-                for (int i = 0; i < n_cols; ++i)
-                    if (kl == nl[(size_t)i] && memcmp(k, names[i], kl) == 0) return;
-                if (any) dst.push_back(',');
-                dst.append(m.lead_b, (size_t)(m.val_e - m.lead_b));   // with the source's own spacing
-                any = true;
-            });
-            for (int i = 0; i < n_cols; ++i) {
-                if (any) dst.push_back(',');
-                dst.push_back('"');
-                dst.append(names[i], nl[(size_t)i]);
-                dst += "\":";
-                const double v = values[(size_t)i * n_rows + rows];
-                if (kinds[i] == OWC_JSONL_INT && std::isfinite(v)) dst += std::to_string((long long)v);
-                else put_double(dst, v);
-                any = true;
-            }
-            dst += "}\n";
-            ++rows;
+        size_t used = 0;
+        render_columns(buf, len, names, kinds, values, n_cols, n_rows, ~size_t(0), [&](const std::string& chunk) {
+            if (used + chunk.size() > out_cap) throw Fail{"jsonl: output buffer too small"};
+            memcpy(out + used, chunk.data(), chunk.size());
+            used += chunk.size();
         });
-        if (rows != n_rows) throw Fail{"jsonl: " + std::to_string(rows) + " rows in the file, " +
-                                       std::to_string(n_rows) + " values per column"};
-        if (dst.size() > out_cap) throw Fail{"jsonl: output buffer too small"};
-        memcpy(out, dst.data(), dst.size());
-        *out_len = dst.size();
+        *out_len = used;
+        return OWC_JSONL_OK;
+    });
+}
+
+int owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                            const double* values, int n_cols, size_t n_rows, const char* out_path) {
+    return guarded([&] {
+        FILE* f = fopen(out_path, "wb");
+        if (!f) throw Fail{std::string("jsonl: cannot open ") + out_path + " for writing"};
+        try {
+            render_columns(buf, len, names, kinds, values, n_cols, n_rows, size_t(4) << 20, [&](const std::string& chunk) {
+                if (fwrite(chunk.data(), 1, chunk.size(), f) != chunk.size())
+                    throw Fail{std::string("jsonl: short write to ") + out_path};
+            });
+        } catch (...) {
+            fclose(f);
+            remove(out_path);
+            throw;
+        }
+        if (fclose(f) != 0) {
+            remove(out_path);
+            throw Fail{std::string("jsonl: cannot finish ") + out_path};
+        }
         return OWC_JSONL_OK;
     });
 }

@@ -183,14 +183,26 @@ def _already_scored(input_file: str, metric_names: list[str]) -> bool:
 
 
 def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> dict:
-    """Native I/O with ``jobs`` THREADS (the scanner runs outside the GIL): all files are parsed up front, scored
-    one after the other in this thread, and rewritten in the background while the next file is being scored."""
+    """Native I/O on worker THREADS (the scanner and the file writer run outside the GIL): a few files are parsed
+    ahead of the one being scored, files are scored one after the other in this thread, and each is rewritten in
+    the background while the next is being scored."""
+    from collections import deque
     from concurrent.futures import ThreadPoolExecutor
 
     results: dict = {}
-    with ThreadPoolExecutor(max_workers=jobs) as pool:
+    # the scanner does ~1 GB/s per thread, so a few workers keep up with the device; more only fight the scoring
+    # thread for the GIL and the tokenizer's threads for cores (8-core host: 3 workers 0.75 s, 16 workers 1.45 s)
+    workers = max(2, min(jobs, 4))
+    ahead = 2                               # parsed files waiting for the device
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        loads: deque = deque()
         writes = []
-        for input_file, loaded in zip(todo, pool.map(_load_items_native, todo), strict=True):
+        nxt = 0
+        for input_file in todo:
+            while nxt < len(todo) and len(loads) < ahead:
+                loads.append(pool.submit(_load_items_native, todo[nxt]))
+                nxt += 1
+            loaded = loads.popleft().result()
             if loaded is None:
                 results[input_file] = score_file(input_file, metric_names)          # pandas path
                 continue
@@ -199,6 +211,7 @@ def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> 
             results[input_file] = outputs
             if columns:
                 writes.append(pool.submit(_write_columns_native, input_file, raw, columns))
+            del raw, items, loaded
         for w in writes:
             w.result()
     return results

@@ -53,16 +53,16 @@ def _raise(rc: int) -> None:
 
 def _extract(raw: bytes, key: str, mode: int) -> list[str]:
     lib = _cabi.lib()
-    out = C.create_string_buffer(len(raw) + 1)
+    out = np.empty(len(raw) + 1, np.uint8)
     out_len, n_rows = C.c_size_t(), C.c_size_t()
-    rc = lib.owc_jsonl_extract(raw, len(raw), key.encode(), mode, out, len(raw) + 1, C.byref(out_len),
+    rc = lib.owc_jsonl_extract(raw, len(raw), key.encode(), mode, out.ctypes.data, len(raw) + 1, C.byref(out_len),
                                C.byref(n_rows))
     if rc != OK:
         _raise(rc)
     if n_rows.value == 0:
         return []
     # one NUL after every row (rows containing NUL were reported as unsupported)
-    return C.string_at(out, out_len.value - 1).decode("utf-8").split("\0")
+    return out[: out_len.value - 1].tobytes().decode("utf-8").split("\0")
 
 
 def count_rows(raw: bytes) -> int:
@@ -75,10 +75,20 @@ def count_rows(raw: bytes) -> int:
 
 def read_pairs(raw: bytes) -> list[tuple[str, str]]:
     """``[(reference string, scored prediction string)]`` per row: what ``_select`` of ``metrics/_group.py`` makes of
-    the ``(target, filtered_resps)`` items the reference builds (``eval_metrics.py:62-70``)."""
-    refs = _extract(raw, "target", FIRST)
-    preds = _extract(raw, "filtered_resps", LAST)
-    return list(zip(refs, preds, strict=True))
+    the ``(target, filtered_resps)`` items the reference builds (``eval_metrics.py:62-70``). One pass over the bytes."""
+    lib = _cabi.lib()
+    cap = len(raw) + 1
+    refs, preds = np.empty(cap, np.uint8), np.empty(cap, np.uint8)       # not zero-filled: pages are touched on write
+    refs_len, preds_len, n_rows = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    rc = lib.owc_jsonl_extract_pairs(raw, len(raw), b"target", b"filtered_resps", refs.ctypes.data, cap, C.byref(refs_len),
+                                     preds.ctypes.data, cap, C.byref(preds_len), C.byref(n_rows))
+    if rc != OK:
+        _raise(rc)
+    if n_rows.value == 0:
+        return []
+    # one NUL after every row (rows containing NUL were reported as unsupported)
+    return list(zip(refs[: refs_len.value - 1].tobytes().decode("utf-8").split("\0"),
+                    preds[: preds_len.value - 1].tobytes().decode("utf-8").split("\0"), strict=True))
 
 
 def has_members(raw: bytes, names: list[str]) -> bool:
@@ -100,32 +110,42 @@ def _column_kind(values) -> int:
     raise Unsupported(f"column of dtype {a.dtype} (only numeric per-row columns are written natively)")
 
 
+def _column_args(raw: bytes, columns: dict):
+    names = list(columns)
+    kinds = (C.c_int32 * len(names))(*[_column_kind(columns[n]) for n in names])
+    vals = [np.asarray(columns[n], dtype=np.float64).reshape(-1) for n in names]
+    n_rows = vals[0].size if vals else count_rows(raw)
+    if any(v.size != n_rows for v in vals):
+        raise ValueError(f"columns of different lengths: {[v.size for v in vals]}")
+    table = np.ascontiguousarray(np.stack(vals)) if vals else np.zeros((0, n_rows))
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    return names, arr, kinds, table, n_rows
+
+
 def render_columns(raw: bytes, columns: dict) -> bytes:
     """The file's bytes with ``columns`` (name -> one number per row) replaced / appended on every line."""
-    names = list(columns)
-    n_rows = count_rows(raw)
-    kinds = (C.c_int32 * len(names))(*[_column_kind(columns[n]) for n in names])
-    vals = np.ascontiguousarray(np.stack([np.asarray(columns[n], dtype=np.float64).reshape(-1) for n in names])
-                                if names else np.zeros((0, n_rows)))
-    if vals.shape != (len(names), n_rows):
-        raise ValueError(f"{n_rows} rows in the file, columns of shape {vals.shape}")
+    names, arr, kinds, table, n_rows = _column_args(raw, columns)
+    if n_rows != count_rows(raw):
+        raise ValueError(f"{count_rows(raw)} rows in the file, {n_rows} values per column")
     cap = len(raw) + n_rows * (sum(len(n.encode()) + 4 for n in names) + 40 * len(names) + 4) + 64
-    out = C.create_string_buffer(cap)
+    out = np.empty(cap, np.uint8)
     out_len = C.c_size_t()
-    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
-    rc = _cabi.lib().owc_jsonl_set_columns(raw, len(raw), arr, kinds, vals.ctypes.data_as(C.c_void_p), len(names),
-                                           n_rows, out, cap, C.byref(out_len))
+    rc = _cabi.lib().owc_jsonl_set_columns(raw, len(raw), arr, kinds, table.ctypes.data_as(C.c_void_p), len(names),
+                                           n_rows, out.ctypes.data, cap, C.byref(out_len))
     if rc != OK:
         _raise(rc)
-    return C.string_at(out, out_len.value)
+    return out[: out_len.value].tobytes()
 
 
 def write_columns(path: str, raw: bytes, columns: dict) -> None:
-    """Rewrite ``path`` with the columns added, through a temporary file (a crash cannot truncate the samples)."""
+    """Rewrite ``path`` with the columns added: the library streams the new text into a temporary file, which then
+    replaces the samples file (a crash cannot truncate it)."""
     if not columns:
         return
-    data = render_columns(raw, columns)
+    names, arr, kinds, table, n_rows = _column_args(raw, columns)
     tmp = path + ".tmp"
-    with open(tmp, "wb") as f:
-        f.write(data)
+    rc = _cabi.lib().owc_jsonl_write_columns(raw, len(raw), arr, kinds, table.ctypes.data_as(C.c_void_p), len(names),
+                                             n_rows, os.fsencode(tmp))
+    if rc != OK:
+        _raise(rc)
     os.replace(tmp, path)

@@ -28,8 +28,8 @@ _THRESHOLDS = [0.5, 0.6, 0.7, 0.8, 0.9]
 
 def _select(items: list) -> tuple[list[str], list[str]]:
     # ref[0] if the reference is a list; pred[-1] (last round wins) - _group.py:515-519
-    refs = list(zip(*items, strict=True))[0]
-    preds = list(zip(*items, strict=True))[1]
+    columns = list(zip(*items, strict=True))      # IndexError on an empty list, like the reference
+    refs, preds = columns[0], columns[1]
     refs = [ref[0] if isinstance(ref, list) else ref for ref in refs]
     preds = [pred[-1] if isinstance(pred, list) else pred for pred in preds]
     return refs, preds

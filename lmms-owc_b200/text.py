@@ -75,13 +75,8 @@ def encode_unique(texts: list[str], rank: int | None = None, out: str = "host"):
     identical, so the host dedups and the paired score indexes into the unique table.
     """
     engine, tok = get_engine(rank)
-    index: dict[str, int] = {}
-    inverse = np.empty(len(texts), dtype=np.int32)
-    for i, t in enumerate(texts):
-        j = index.get(t)
-        if j is None:
-            j = index[t] = len(index)
-        inverse[i] = j
+    index = {t: i for i, t in enumerate(dict.fromkeys(texts))}     # first occurrence order
+    inverse = np.fromiter(map(index.__getitem__, texts), dtype=np.int32, count=len(texts))
     ids, cu = tok.encode_packed(list(index))
     return engine.encode(ids, cu, out=out), inverse
 
