@@ -72,7 +72,7 @@ struct owc_ctx {
   int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
   int pdl = 1;             // programmatic dependent launch between the kernels of a layer (env OWC_PDL)
   int fused = 1;           // block-resident fused encoder for MiniLM-width BERT, sequences <= 64 tokens (env OWC_FUSED)
-  int fused_waves = 16;    // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES)
+  int fused_waves = 48;    // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES): one launch per 100 k-row step
   int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
