@@ -311,6 +311,7 @@ def main(args: Namespace) -> dict:
         from . import text as _text
 
         _text.default_rank = local_rank
+        os.environ.setdefault("OWC_TOKENIZER_THREADS", str(max(1, (os.cpu_count() or 1) // world)))   # share the host
         mine = split_files_balanced(input_files, world)[rank]
         log.info("Rank %d/%d scores %d of the files", rank, world, len(mine))
     per_file = score_files(mine, args.metrics.split(","), jobs=getattr(args, "jobs", 1),

@@ -138,7 +138,8 @@ class HostTokenizer:
         use_native = self._native is not None if native is None else (native and self._native is not None)
         if not use_native or not texts:
             return pack_ids(self.encode_ragged(texts))
-        ids, lens = self._native.tokenize(texts)
+        # 0 = every core; several ranks on one host share the cores (OWC_TOKENIZER_THREADS, set by the multi-rank CLI)
+        ids, lens = self._native.tokenize(texts, threads=int(os.environ.get("OWC_TOKENIZER_THREADS", "0")))
         flagged = np.nonzero(lens < 0)[0]
         if flagged.size == 0:
             cu = np.zeros(len(texts) + 1, dtype=np.int64)

@@ -45,40 +45,66 @@ def write_logs(root: str, n_models: int, words) -> int:
 if __name__ == "__main__":
     n_models = int(sys.argv[1]) if len(sys.argv) > 1 else 13
     modes = (sys.argv[2] if len(sys.argv) > 2 else "native,pandas").split(",")
+    # under torchrun: one process per GPU, files dealt to the ranks by eval_metrics.main; rank 0 writes the logs
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
     arch = A.MINILM_L6
     vocab = synth.build_vocab("bert", arch.vocab)
     words = synth.vocab_words(vocab)
-    T.configure(arch, random_state_dict(arch), vocab, device=0)
-    base = tempfile.mkdtemp()
+    T.configure(arch, random_state_dict(arch), vocab, device=local_rank)
+    base = tempfile.mkdtemp() if world == 1 else os.path.join(tempfile.gettempdir(), f"owc_cli_bench_{os.environ.get('MASTER_PORT', '0')}")
     src = os.path.join(base, "src", "logs")
-    t0 = time.perf_counter()
-    total = write_logs(src, n_models, words)
-    size = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(src) for f in fs)
-    print(f"wrote {n_models * len(TEST_ROWS)} files, {total} rows, {size / 1e6:.0f} MB in {time.perf_counter() - t0:.1f}s", file=sys.stderr)
-    # warm-up: one small task end to end (first launches, tokenizer threads, pandas import)
-    warm = os.path.join(base, "warm", "logs")
+    warm = os.path.join(base, f"warm{rank}", "logs")
+    total = size = 0
+    if rank == 0:
+        shutil.rmtree(base, ignore_errors=True)
+        t0 = time.perf_counter()
+        total = write_logs(src, n_models, words)
+        size = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(src) for f in fs)
+        print(f"wrote {n_models * len(TEST_ROWS)} files, {total} rows, {size / 1e6:.0f} MB in {time.perf_counter() - t0:.1f}s", file=sys.stderr)
+        for mode in modes:
+            shutil.copytree(src, os.path.join(base, mode, "logs"))
+    if world > 1:
+        dist.barrier()
+    # warm-up on this rank's GPU: one small task end to end, outside the multi-rank dealing
     shutil.copytree(os.path.join(src, "dtd"), os.path.join(warm, "dtd"))
-    EM.main(EM.build_parser().parse_args(["-i", warm, "-m", "semantic_similarity", "--io", "native", "--log-level", "WARNING"]))
+    saved = os.environ.pop("WORLD_SIZE", None)
+    import contextlib
+    import io as _io
+    with contextlib.redirect_stdout(_io.StringIO()):
+        EM.main(EM.build_parser().parse_args(["-i", warm, "-m", "semantic_similarity", "--io", "native", "--log-level", "WARNING"]))
+    if saved is not None:
+        os.environ["WORLD_SIZE"] = saved
     out = {"workload": f"c5 through the CLI mirror: {n_models} models x 10 tasks = {n_models * len(TEST_ROWS)} files, {total} rows, "
-                       f"{size / 1e6:.0f} MB of JSONL; eval_metrics -m semantic_similarity (files -> paired scores -> files rewritten), 1 GPU",
-           "rows": total}
+                       f"{size / 1e6:.0f} MB of JSONL; eval_metrics -m semantic_similarity (files -> paired scores -> files rewritten), "
+                       f"{world} GPU(s), one process each",
+           "rows": total, "n_gpus": world}
     results = {}
     for mode in modes:
         work = os.path.join(base, mode, "logs")
-        shutil.copytree(src, work)
         argv = ["-i", work, "-m", "semantic_similarity", "--io", mode, "--jobs", "16", "--log-level", "WARNING"]
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        import contextlib
-        import io as _io
         with contextlib.redirect_stdout(_io.StringIO()):
-            results[mode] = EM.main(EM.build_parser().parse_args(argv))
+            results[mode] = EM.main(EM.build_parser().parse_args(argv))      # gathers on rank 0 when world > 1
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        out[mode] = {"seconds": dt, "rows_per_s": total / dt, "args": " ".join(argv[2:])}
-    if len(results) == 2:
-        a, b = (results[m] for m in modes)
-        out["same_outputs"] = a == b
-    print(json.dumps(out))
-    shutil.rmtree(base, ignore_errors=True)
+        if rank == 0:
+            out[mode] = {"seconds": dt, "rows_per_s": total / dt, "args": " ".join(argv[2:])}
+    if rank == 0:
+        if len(results) == 2:
+            a, b = (results[m] for m in modes)
+            out["same_outputs"] = a == b
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        shutil.rmtree(base, ignore_errors=True)
     T.reset()
