@@ -84,6 +84,17 @@ if __name__ == "__main__":
                        f"{world} GPU(s), one process each",
            "rows": total, "n_gpus": world}
     results = {}
+    _score_files = EM.score_files
+
+    def timed_score_files(files, *a, **k):          # per-rank view: own files only, before the gather
+        t = time.perf_counter()
+        try:
+            return _score_files(files, *a, **k)
+        finally:
+            torch.cuda.synchronize()
+            print(f"rank {rank}: {len(files)} files scored in {time.perf_counter() - t:.2f}s", file=sys.stderr, flush=True)
+
+    EM.score_files = timed_score_files
     for mode in modes:
         work = os.path.join(base, mode, "logs")
         argv = ["-i", work, "-m", "semantic_similarity", "--io", mode, "--jobs", "16", "--log-level", "WARNING"]
