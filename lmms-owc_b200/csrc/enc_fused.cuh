@@ -568,7 +568,6 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
       if (lane == 0) arrive_leader(xb_ready);
     };
-    // LayerNorm of (x + bias) over the row, in place; optionally stores the fp32 row to global (last layer)
     // LayerNorm of (x + bias) over the row, in place (x in TMEM + XB); the block's last one writes the fp32 row
     // to global instead. Two passes over TMEM (statistics, then normalise) in packed fp32x2 arithmetic; the
     // NW warps of a lane quadrant each own every NW-th 32-column chunk and exchange partial statistics.

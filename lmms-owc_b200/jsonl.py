@@ -29,7 +29,7 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["JsonlError", "Unsupported", "read_pairs", "render_columns", "write_columns", "has_members", "count_rows"]
+__all__ = ["JsonlError", "Unsupported", "read_pairs", "read_strings", "render_columns", "write_columns", "has_members", "count_rows"]
 
 OK, ERROR, UNSUPPORTED = 0, 1, 2
 FIRST, LAST = 0, 1
@@ -51,7 +51,9 @@ def _raise(rc: int) -> None:
     raise JsonlError(msg)
 
 
-def _extract(raw: bytes, key: str, mode: int) -> list[str]:
+def read_strings(raw: bytes, key: str, mode: int) -> list[str]:
+    """One string per row from top-level member ``key`` (``mode``: ``FIRST`` = reference rule, ``LAST`` = scored
+    prediction rule); ``owc_jsonl_extract``."""
     lib = _cabi.lib()
     out = np.empty(len(raw) + 1, np.uint8)
     out_len, n_rows = C.c_size_t(), C.c_size_t()

@@ -110,6 +110,21 @@ def test_reader_rejects_malformed_lines_with_the_line_number(line, where):
         jsonl.read_pairs(b'{"target":"ok","filtered_resps":["fine"]}\n' + line + b"\n")
 
 
+def test_single_member_reader_agrees_with_the_pair_reader():
+    from owc_b200 import jsonl
+
+    rows = [r for r in _rows(60) if not isinstance(r["filtered_resps"][0], list)]
+    raw = "\n".join(json.dumps(r) for r in rows).encode()
+    pairs = jsonl.read_pairs(raw)
+    assert jsonl.read_strings(raw, "target", jsonl.FIRST) == [p[0] for p in pairs]
+    assert jsonl.read_strings(raw, "filtered_resps", jsonl.LAST) == [p[1] for p in pairs]
+    assert jsonl.read_strings(raw, "input", jsonl.FIRST) == ["What?"] * len(rows)
+    with pytest.raises(jsonl.Unsupported):
+        jsonl.read_strings(raw, "doc_id", jsonl.FIRST)            # a number, not a string
+    with pytest.raises(jsonl.JsonlError):
+        jsonl.read_strings(raw, "target", 7)
+
+
 def test_reader_decodes_escapes_like_json():
     from owc_b200 import jsonl
 
