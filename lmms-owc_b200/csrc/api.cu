@@ -72,6 +72,7 @@ struct owc_ctx {
   int ares = 1;            // 1-CTA kernel keeps the A block resident in shared memory when K <= 384 (env OWC_ARES)
   int pdl = 1;             // programmatic dependent launch between the kernels of a layer (env OWC_PDL)
   int fused = 1;           // block-resident fused encoder for MiniLM-width BERT, sequences <= 64 tokens (env OWC_FUSED)
+  int enc_wide = 1;        // 256-column tiles for wide encoders (env OWC_ENC_WIDE=0: kEncBN tiles everywhere)
   int fused_waves = 48;    // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES): one launch per 100 k-row step
   int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
   int sm_count = 0;
@@ -92,6 +93,7 @@ struct LayerW {
   const __nv_bfloat16 *wqkv, *wo, *w1, *w2;                        // bf16 operand copies
   CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;          // W maps, box = kEncBN rows (1-CTA kernel)
   CUtensorMap tm2_wqkv, tm2_wo, tm2_w1, tm2_w2;      // W maps, box = kEncBN/2 rows (CTA-pair kernel)
+  CUtensorMap tmw_wqkv, tmw_wo, tmw_w1, tmw_w2;      // W maps, box = 128 rows (CTA-pair kernel, 256-column tiles; wide encoders)
 };
 
 struct owc_encoder {
@@ -112,6 +114,7 @@ struct owc_encoder {
   bool fused_ok = false;
   __nv_bfloat16 *fw_qkv = nullptr, *fw_o = nullptr, *fw_1 = nullptr, *fw_2 = nullptr;
   CUtensorMap tmf_qkv, tmf_o, tmf_1, tmf_2;
+  bool wide = false;               // every GEMM width is a multiple of 256 (mpnet-base: 2304 / 768 / 3072): 256-column tiles
   int fcap = 0;                    // tokens per fused launch
   float* fx = nullptr;             // [fcap + 128, H] fp32 residual stream of a fused chunk
   long long* fdbg = nullptr;       // [1024] timeline stamps + event traces
@@ -315,6 +318,18 @@ static int launch_gemm(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb_
   return launch_gemm_tc2<BN, EPI, KC, false>(c, ta, tb_half, tc, g, splits);
 }
 
+// Encoder contraction: 256-column tiles on CTA pairs where the encoder is wide enough for pairs to win and every width
+// divides (UMMA N = 256 is the shape whose operand fetch keeps up with the tensor pipe; measured on the mpnet-base
+// shapes against N = 192: +2.4 % QKV, +1 % O, +2.6 % FFN1, +11.6 % FFN2), the kEncBN kernels otherwise.
+template <int EPI>
+static int launch_enc_gemm(owc_ctx* c, bool wide, const CUtensorMap& ta, const CUtensorMap& tb_full, const CUtensorMap& tb_half,
+                           const CUtensorMap& tb_wide, const CUtensorMap& tc, const GemmArgs& g) {
+  const int mode = c->gemm_mode >= 0 ? c->gemm_mode : ((g.K >= 768 || g.N >= 2304) ? 1 : 0);
+  if (wide && c->enc_wide && mode != 0)
+    return launch_gemm_tc2<256, EPI, 1, false>(c, ta, tb_wide, tc, g, pick_splits(c, g.M, g.N, 256));
+  return launch_gemm<kEncBN, EPI, 1>(c, ta, tb_full, tb_half, tc, g);
+}
+
 template <int EPF>
 static int launch_gemm_f32(owc_ctx* c, const float* A, const float* W, const float* bias, const float* res, float* out,
                            int M, int N, int K, int ldo) {
@@ -371,6 +386,7 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* ar = getenv("OWC_ARES")) c->ares = atoi(ar) != 0;
   if (const char* pd = getenv("OWC_PDL")) c->pdl = atoi(pd) != 0;
   if (const char* fu = getenv("OWC_FUSED")) c->fused = atoi(fu) != 0;
+  if (const char* ew = getenv("OWC_ENC_WIDE")) c->enc_wide = atoi(ew) != 0;
   if (const char* fw = getenv("OWC_FUSED_WAVES")) c->fused_waves = std::max(1, std::min(64, atoi(fw)));
   if (const char* fd = getenv("OWC_FUSED_DBG")) c->fused_dbg = atoi(fd) != 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
@@ -517,6 +533,7 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   e->arch = a;
   e->cap = c->chunk_tokens;
   const size_t h = a.hidden, I = a.inter;
+  e->wide = h >= 768 && h % 256 == 0 && I % 256 == 0;
 #define LOAD_FAIL(...) do { int _r = fail(__VA_ARGS__); owc_encoder_destroy(e); return _r; } while (0)
 #define LOAD_CU(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) LOAD_FAIL("%s failed: %s", #expr, cudaGetErrorString(_e)); } while (0)
   LOAD_CU(cudaMalloc(&e->w32, n_floats * sizeof(float)));
@@ -560,6 +577,9 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
         make_tmap(c, &L.tm_w1, L.w1, I, h, kEncBN) || make_tmap(c, &L.tm_w2, L.w2, h, I, kEncBN)) { owc_encoder_destroy(e); return 1; }
     if (make_tmap(c, &L.tm2_wqkv, L.wqkv, 3 * h, h, kEncBN / 2) || make_tmap(c, &L.tm2_wo, L.wo, h, h, kEncBN / 2) ||
         make_tmap(c, &L.tm2_w1, L.w1, I, h, kEncBN / 2) || make_tmap(c, &L.tm2_w2, L.w2, h, I, kEncBN / 2)) { owc_encoder_destroy(e); return 1; }
+    if (e->wide &&
+        (make_tmap(c, &L.tmw_wqkv, L.wqkv, 3 * h, h, 128) || make_tmap(c, &L.tmw_wo, L.wo, h, h, 128) ||
+         make_tmap(c, &L.tmw_w1, L.w1, I, h, 128) || make_tmap(c, &L.tmw_w2, L.w2, h, I, 128))) { owc_encoder_destroy(e); return 1; }
   }
   if (static_cast<size_t>(p - e->w32) != n_floats) LOAD_FAIL("internal: blob walk mismatch");
 
@@ -737,7 +757,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
     if (bf) {
       GemmArgs g{};
       g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
-      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_BF16, 1>(c, e->tm_xb, L.tm_wqkv, L.tm2_wqkv, e->tmo_qkv, g)));
+      OWC_TRY((launch_enc_gemm<EPI_BIAS_BF16>(c, e->wide, e->tm_xb, L.tm_wqkv, L.tm2_wqkv, L.tmw_wqkv, e->tmo_qkv, g)));
       aa.qkv = e->qkv; aa.out = e->ao;
       if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
       else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
@@ -748,7 +768,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
         OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_ao, L.tm_wo, e->tmo_x, g, 1, &e->tmo_xb)));
       } else {
         g.residual = e->x; g.ldo = H;
-        OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_ao, L.tm_wo, L.tm2_wo, e->tmo_y, g)));
+        OWC_TRY((launch_enc_gemm<EPI_BIAS_RES_F32>(c, e->wide, e->tm_ao, L.tm_wo, L.tm2_wo, L.tmw_wo, e->tmo_y, g)));
       }
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS>(c, e->x, L.wqkv32, L.bqkv, nullptr, e->qkv32, M, 3 * H, H, 3 * H));
@@ -767,7 +787,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
     if (bf) {
       GemmArgs g{};
       g.M = M; g.N = I; g.K = H; g.bias = L.b1;
-      OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_GELU_BF16, 1>(c, e->tm_xb, L.tm_w1, L.tm2_w1, e->tmo_f, g)));
+      OWC_TRY((launch_enc_gemm<EPI_BIAS_GELU_BF16>(c, e->wide, e->tm_xb, L.tm_w1, L.tm2_w1, L.tmw_w1, e->tmo_f, g)));
       g = GemmArgs{};
       g.M = M; g.N = H; g.K = I; g.bias = L.b2;
       if (fuse_ln) {
@@ -775,7 +795,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
         OWC_TRY((launch_gemm_tc<kEncBN, EPI_RES_LN, 1>(c, e->tm_f, L.tm_w2, e->tmo_x, g, 1, &e->tmo_xb)));
       } else {
         g.residual = e->x; g.ldo = H;
-        OWC_TRY((launch_gemm<kEncBN, EPI_BIAS_RES_F32, 1>(c, e->tm_f, L.tm_w2, L.tm2_w2, e->tmo_y, g)));
+        OWC_TRY((launch_enc_gemm<EPI_BIAS_RES_F32>(c, e->wide, e->tm_f, L.tm_w2, L.tm2_w2, L.tmw_w2, e->tmo_y, g)));
       }
     } else {
       OWC_TRY(launch_gemm_f32<EPF_BIAS_GELU>(c, e->x, L.w132, L.b1, nullptr, e->f32, M, I, H, I));
