@@ -39,14 +39,22 @@ for ti, (ds, rows) in enumerate(TEST_ROWS.items()):
         files[f"model{m:02d}"] = {"predictions": preds, "targets": targets}
     tasks[ds] = {"class_names": names, "files": files}
 total = sum(len(f["predictions"]) for t in tasks.values() for f in t["files"].values())
-score_sweep(eng, tok, {k: v for k, v in list(tasks.items())[:2]}, k=5)      # warm-up
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-res = score_sweep(eng, tok, tasks, k=5)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+# warm-up: every class-set size once (each picks its own kernel variants; CUDA loads a kernel on its first launch),
+# then one full-size task for the buffers
+score_sweep(eng, tok, {ds: {"class_names": t["class_names"],
+                            "files": {"w": {"predictions": t["files"]["model00"]["predictions"][:512],
+                                            "targets": t["files"]["model00"]["targets"][:512]}}} for ds, t in tasks.items()}, k=5)
+score_sweep(eng, tok, {k: v for k, v in list(tasks.items())[:2]}, k=5)
+runs = []
+for _ in range(3):      # the first full pass on a fresh box runs ~2x slower than the following ones; all are reported
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = score_sweep(eng, tok, tasks, k=5)
+    torch.cuda.synchronize()
+    runs.append(time.perf_counter() - t0)
+dt = min(runs)
 acc = {ds: float(np.mean([np.mean(res[ds][k]["idx"][:, 0] == np.asarray(tasks[ds]["files"][k]["targets"])) for k in res[ds]])) for ds in res}
 print(json.dumps({"workload": f"c5: {n_models} models x 10 tasks, {total} predictions, strings -> top-5 + paired score, 1 GPU",
-                  "seconds": dt, "predictions_per_s": total / dt, "files": n_models * len(TEST_ROWS),
+                  "seconds": dt, "seconds_per_pass": runs, "predictions_per_s": total / dt, "files": n_models * len(TEST_ROWS),
                   "class_sets": {ds: len(t["class_names"]) for ds, t in tasks.items()}, "top1_vs_random_targets": acc}))
 eng.close()
