@@ -63,6 +63,7 @@ struct owc_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int chunk_tokens = 0;
+  bool chunk_default = true;   // chunk_tokens was not given: encoders pick their own multiple of one block per SM
   // tcgen05 kernel variant: 0 = one CTA per 128 rows, 1 = CTA pairs (cta_group::2), 2 = CTA pairs + resident A.
   // Measured on B200: the encoder's short sweeps (2-8 column tiles per row block) run fastest on the 1-CTA
   // kernel, the similarity sweep (hundreds of tiles) on pairs with the A block resident.
@@ -389,6 +390,7 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* ew = getenv("OWC_ENC_WIDE")) c->enc_wide = atoi(ew) != 0;
   if (const char* fw = getenv("OWC_FUSED_WAVES")) c->fused_waves = std::max(1, std::min(64, atoi(fw)));
   if (const char* fd = getenv("OWC_FUSED_DBG")) c->fused_dbg = atoi(fd) != 0;
+  c->chunk_default = chunk_tokens <= 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -531,7 +533,9 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   if (!e) return fail("out of host memory");
   e->ctx = c;
   e->arch = a;
-  e->cap = c->chunk_tokens;
+  // one 128-row block per SM; wide encoders (CTA-pair GEMMs) run two waves per launch (measured on mpnet-base:
+  // 129.1 ms per c3 step against 132.5 ms; more than two changes nothing)
+  e->cap = (c->chunk_default && a.hidden >= 768) ? 2 * c->chunk_tokens : c->chunk_tokens;
   const size_t h = a.hidden, I = a.inter;
   e->wide = h >= 768 && h % 256 == 0 && I % 256 == 0;
 #define LOAD_FAIL(...) do { int _r = fail(__VA_ARGS__); owc_encoder_destroy(e); return _r; } while (0)
