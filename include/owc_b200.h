@@ -211,6 +211,11 @@ int32_t owc_jsonl_extract(const char* buf, size_t len, const char* key, int32_t 
 int32_t owc_jsonl_extract_pairs(const char* buf, size_t len, const char* ref_key, const char* pred_key, char* out_refs,
                                 size_t refs_cap, size_t* refs_len, char* out_preds, size_t preds_cap,
                                 size_t* preds_len, size_t* n_rows);
+/* Distinct strings of a blob of n NUL-terminated rows (the format the two extractors write), in first-occurrence order,
+ * into out (cap >= len suffices) + inverse int32 [n] (row -> index of its string): the dedup of text.encode_unique
+ * without a Python object per row.                                                                              */
+int32_t owc_blob_unique(const char* blob, size_t len, size_t n, int32_t* inverse, char* out, size_t out_cap,
+                        size_t* out_len, size_t* n_unique);
 /* *all_rows = 1 iff the buffer has at least one row and every row carries every member of names[].               */
 int32_t owc_jsonl_has_members(const char* buf, size_t len, const char* const* names, int32_t n_names,
                               int32_t* all_rows);

@@ -476,6 +476,51 @@ int owc_jsonl_extract_pairs(const char* buf, size_t len, const char* ref_key, co
     });
 }
 
+int owc_blob_unique(const char* blob, size_t len, size_t n, int32_t* inverse, char* out, size_t out_cap, size_t* out_len,
+                    size_t* n_unique) {
+    return guarded([&] {
+        // rows: n NUL-terminated strings back to back (what owc_jsonl_extract* write); first-occurrence order is kept
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        std::vector<int64_t> slot(cap, -1);               // offset of the unique string in `out`, -1 = empty
+        std::vector<int32_t> slot_id(cap, 0);
+        size_t used = 0, uniq = 0;
+        const char* p = blob;
+        const char* e = blob + len;
+        for (size_t i = 0; i < n; ++i) {
+            if (p >= e) throw Fail{"blob: fewer rows than announced"};
+            const char* z = (const char*)memchr(p, 0, (size_t)(e - p));
+            if (!z) throw Fail{"blob: missing terminator"};
+            const size_t l = (size_t)(z - p);
+            uint64_t h = 1469598103934665603ull;            // FNV-1a
+            for (size_t j = 0; j < l; ++j) h = (h ^ (unsigned char)p[j]) * 1099511628211ull;
+            size_t k = (size_t)(h ^ (h >> 29)) & (cap - 1);
+            for (;;) {
+                if (slot[k] < 0) {
+                    if (used + l + 1 > out_cap) throw Fail{"blob: output buffer too small"};
+                    memcpy(out + used, p, l + 1);
+                    slot[k] = (int64_t)used;
+                    slot_id[k] = (int32_t)uniq;
+                    inverse[i] = (int32_t)uniq;
+                    used += l + 1;
+                    ++uniq;
+                    break;
+                }
+                const char* q = out + slot[k];
+                if (strlen(q) == l && memcmp(q, p, l) == 0) {
+                    inverse[i] = slot_id[k];
+                    break;
+                }
+                k = (k + 1) & (cap - 1);
+            }
+            p = z + 1;
+        }
+        *out_len = used;
+        *n_unique = uniq;
+        return OWC_JSONL_OK;
+    });
+}
+
 int owc_jsonl_has_members(const char* buf, size_t len, const char* const* names, int n_names, int* all_rows) {
     return guarded([&] {
         std::vector<size_t> nl((size_t)n_names);

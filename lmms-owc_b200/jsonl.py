@@ -29,7 +29,7 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["JsonlError", "Unsupported", "read_pairs", "read_strings", "render_columns", "write_columns", "has_members", "count_rows"]
+__all__ = ["JsonlError", "Unsupported", "PackedPairs", "PackedStrings", "read_packed_pairs", "read_pairs", "read_strings", "render_columns", "write_columns", "has_members", "count_rows"]
 
 OK, ERROR, UNSUPPORTED = 0, 1, 2
 FIRST, LAST = 0, 1
@@ -91,6 +91,67 @@ def read_pairs(raw: bytes) -> list[tuple[str, str]]:
     # one NUL after every row (rows containing NUL were reported as unsupported)
     return list(zip(refs[: refs_len.value - 1].tobytes().decode("utf-8").split("\0"),
                     preds[: preds_len.value - 1].tobytes().decode("utf-8").split("\0"), strict=True))
+
+
+class PackedStrings:
+    """``n`` strings as one UTF-8 blob, each followed by a NUL byte (the scanner's own output format)."""
+
+    __slots__ = ("blob", "n")
+
+    def __init__(self, blob: bytes, n: int) -> None:
+        self.blob, self.n = blob, n
+
+    def __len__(self) -> int:
+        return self.n
+
+    def tolist(self) -> list[str]:
+        return self.blob[:-1].decode("utf-8").split("\0") if self.n else []
+
+    def unique(self) -> tuple["PackedStrings", np.ndarray]:
+        """``(distinct strings in first-occurrence order, inverse int32 [n])`` - ``owc_blob_unique``."""
+        inverse = np.empty(self.n, dtype=np.int32)
+        if self.n == 0:
+            return PackedStrings(b"", 0), inverse
+        out = np.empty(len(self.blob) + 1, np.uint8)
+        out_len, n_unique = C.c_size_t(), C.c_size_t()
+        rc = _cabi.lib().owc_blob_unique(self.blob, len(self.blob), self.n, inverse.ctypes.data, out.ctypes.data,
+                                         len(self.blob) + 1, C.byref(out_len), C.byref(n_unique))
+        if rc != OK:
+            _raise(rc)
+        return PackedStrings(out[: out_len.value].tobytes(), n_unique.value), inverse
+
+
+class PackedPairs:
+    """The ``(reference, prediction)`` items of one samples file in packed form. Stands in for the list of tuples the
+    reference builds (``eval_metrics.py:70``) on the CLI's native path only: ``len()`` works, the group metrics pick
+    the two columns up without touching a row, ``tolist()`` gives the ordinary items."""
+
+    __slots__ = ("refs", "preds")
+
+    def __init__(self, refs: PackedStrings, preds: PackedStrings) -> None:
+        if len(refs) != len(preds):
+            raise ValueError("one reference per prediction")
+        self.refs, self.preds = refs, preds
+
+    def __len__(self) -> int:
+        return len(self.refs)
+
+    def tolist(self) -> list[tuple[str, str]]:
+        return list(zip(self.refs.tolist(), self.preds.tolist(), strict=True))
+
+
+def read_packed_pairs(raw: bytes) -> PackedPairs:
+    """:func:`read_pairs` without making a Python string per row."""
+    lib = _cabi.lib()
+    cap = len(raw) + 1
+    refs, preds = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    refs_len, preds_len, n_rows = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    rc = lib.owc_jsonl_extract_pairs(raw, len(raw), b"target", b"filtered_resps", refs.ctypes.data, cap, C.byref(refs_len),
+                                     preds.ctypes.data, cap, C.byref(preds_len), C.byref(n_rows))
+    if rc != OK:
+        _raise(rc)
+    n = n_rows.value
+    return PackedPairs(PackedStrings(refs[: refs_len.value].tobytes(), n), PackedStrings(preds[: preds_len.value].tobytes(), n))
 
 
 def has_members(raw: bytes, names: list[str]) -> bool:

@@ -28,6 +28,8 @@ _THRESHOLDS = [0.5, 0.6, 0.7, 0.8, 0.9]
 
 def _select(items: list) -> tuple[list[str], list[str]]:
     # ref[0] if the reference is a list; pred[-1] (last round wins) - _group.py:515-519
+    if hasattr(items, "refs") and hasattr(items, "preds"):      # jsonl.PackedPairs: the scanner applied both rules already
+        return items.refs, items.preds
     columns = list(zip(*items, strict=True))      # IndexError on an empty list, like the reference
     refs, preds = columns[0], columns[1]
     refs = [ref[0] if isinstance(ref, list) else ref for ref in refs]
@@ -37,7 +39,15 @@ def _select(items: list) -> tuple[list[str], list[str]]:
 
 def _paired_scores(refs: list[str], preds: list[str]) -> np.ndarray:
     """``s_i = <z(ref_i), z(pred_i)>`` (the ``torch.bmm`` of _group.py:537-544), fp32 [N]."""
-    engine, _ = _text.get_engine()
+    engine, tok = _text.get_engine()
+    if hasattr(refs, "blob") and hasattr(preds, "blob"):        # jsonl.PackedStrings: dedup + tokenisation without Python rows
+        tables = []
+        for col in (refs, preds):
+            uniq, inverse = col.unique()
+            ids, cu = tok.encode_packed_blob(uniq.blob[:-1], uniq.n)
+            tables.append((engine.encode(ids, cu, out="device"), inverse))
+        (zr, ridx), (zp, pidx) = tables
+        return engine.pair_dot(zr, zp, a_index=ridx, b_index=pidx)
     # embeddings stay in device memory between the two calls: only token ids / indices go up and N scores come down
     zr, ridx = _text.encode_unique(refs, out="device")
     zp, pidx = _text.encode_unique(preds, out="device")

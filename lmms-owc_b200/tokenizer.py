@@ -83,6 +83,22 @@ class NativeWordPiece:
         return ids[: n_ids.value], lens
 
 
+    def tokenize_blob(self, blob: bytes, n: int, threads: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """Same as :meth:`tokenize` for ``n`` rows already joined by NUL bytes (no trailing NUL, no NUL inside a row):
+        the bytes go to the library as they are, no Python string is made."""
+        from . import _cabi
+
+        cap = len(blob) + 2 * n + 1
+        ids = np.empty(cap, dtype=np.int32)
+        lens = np.empty(n, dtype=np.int32)
+        n_ids = C.c_int64(0)
+        rc = self._lib.owc_tokenize_packed(self._h, blob, None, n, int(threads), ids.ctypes.data, cap, lens.ctypes.data,
+                                           C.byref(n_ids))
+        if rc != 0:
+            raise _cabi.OwcError(self._lib.owc_tokenizer_last_error().decode("utf-8", "replace"))
+        return ids[: n_ids.value], lens
+
+
 class HostTokenizer:
     """WordPiece tokenizer over an in-memory vocabulary: the library's native C++ path for ASCII rows
     (``NativeWordPiece``), the ``tokenizers`` backend for everything else and as the cross-check."""
@@ -140,23 +156,43 @@ class HostTokenizer:
             return pack_ids(self.encode_ragged(texts))
         # 0 = every core; several ranks on one host share the cores (OWC_TOKENIZER_THREADS, set by the multi-rank CLI)
         ids, lens = self._native.tokenize(texts, threads=int(os.environ.get("OWC_TOKENIZER_THREADS", "0")))
+        return self._finish_native(ids, lens, lambda rows: [texts[i] for i in rows])
+
+    def encode_packed_blob(self, blob: bytes, n: int) -> tuple[np.ndarray, np.ndarray]:
+        """:meth:`encode_packed` for ``n`` UTF-8 rows joined by NUL bytes (the JSONL scanner's output minus its last
+        terminator): same ids, but only the rows the native path flags ever become Python strings."""
+        if n == 0:
+            return pack_ids([])
+        if self._native is None:
+            return self.encode_packed(blob.decode("utf-8").split("\0"))
+        ids, lens = self._native.tokenize_blob(blob, n, threads=int(os.environ.get("OWC_TOKENIZER_THREADS", "0")))
+
+        def rows_of(rows):
+            parts = blob.split(b"\0")
+            return [parts[i].decode("utf-8") for i in rows]
+
+        return self._finish_native(ids, lens, rows_of)
+
+    def _finish_native(self, ids, lens, texts_of) -> tuple[np.ndarray, np.ndarray]:
+        """cu_seqlens from the native lengths; rows it flagged (-1) are tokenised by the backend and spliced in."""
+        n = len(lens)
         flagged = np.nonzero(lens < 0)[0]
         if flagged.size == 0:
-            cu = np.zeros(len(texts) + 1, dtype=np.int64)
+            cu = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(lens, out=cu[1:])
             if cu[-1] >= 2**31:
                 raise ValueError("packed batch exceeds 2^31 tokens; split it")
             return ids, cu.astype(np.int32)
         # splice the rows the native path left to the backend (non-ASCII, literal special tokens) back in
-        extra = self.encode_ragged([texts[i] for i in flagged])
+        extra = self.encode_ragged(texts_of(flagged))
         lens = lens.astype(np.int64)
         lens[flagged] = [len(e) for e in extra]
-        cu = np.zeros(len(texts) + 1, dtype=np.int64)
+        cu = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=cu[1:])
         if cu[-1] >= 2**31:
             raise ValueError("packed batch exceeds 2^31 tokens; split it")
         out = np.empty(int(cu[-1]), dtype=np.int32)
-        is_extra = np.zeros(len(texts), dtype=bool)
+        is_extra = np.zeros(n, dtype=bool)
         is_extra[flagged] = True
         tok_extra = np.repeat(is_extra, lens)
         out[~tok_extra] = ids

@@ -309,3 +309,30 @@ def test_cli_native_io_scores_like_the_pandas_path(minilm, monkeypatch, tmp_path
     assert not EM._native_eligible(["concept_semantic_similarity"])
     with pytest.raises(ValueError):
         EM.score_files([], ["semantic_similarity"], io="arrow")
+
+
+def test_packed_route_equals_the_string_route():
+    """The CLI's packed columns (scanner blob -> native dedup -> native tokenizer) carry exactly what the string route
+    (read_pairs -> text.encode_unique -> encode_packed) carries: same distinct strings, same inverse, same ids."""
+    from owc_b200 import jsonl, synth
+    from owc_b200.tokenizer import HostTokenizer
+
+    vocab = synth.build_vocab("bert", 30522)
+    tok = HostTokenizer(vocab, "bert")
+    words = synth.vocab_words(vocab)
+    texts = [" ".join(words[(7 * i + j) % 997] for j in range(1 + i % 5)) for i in range(400)]
+    texts += ["", "café au lait", "a [SEP] b", "dup", "dup", "日本 語", "", "x" * 700]      # flagged rows, repeats, empties
+    rows = [{"target": texts[(3 * i) % 17], "filtered_resps": [texts[i]]} for i in range(len(texts))]
+    raw = "\n".join(json.dumps(r, ensure_ascii=bool(i % 2)) for i, r in enumerate(rows)).encode()
+    packed = jsonl.read_packed_pairs(raw)
+    assert len(packed) == len(rows) and packed.tolist() == jsonl.read_pairs(raw)
+    for col, strings in ((packed.refs, [r["target"] for r in rows]), (packed.preds, texts)):
+        uniq, inverse = col.unique()
+        first_seen = list(dict.fromkeys(strings))
+        assert uniq.tolist() == first_seen and uniq.n == len(first_seen)
+        assert [first_seen[i] for i in inverse] == strings
+        ids_a, cu_a = tok.encode_packed_blob(uniq.blob[:-1], uniq.n)
+        ids_b, cu_b = tok.encode_packed(first_seen)
+        assert np.array_equal(cu_a, cu_b) and np.array_equal(ids_a, ids_b)
+    empty = jsonl.PackedStrings(b"", 0)
+    assert empty.tolist() == [] and empty.unique()[0].n == 0 and tok.encode_packed_blob(b"", 0)[1].tolist() == [0]
