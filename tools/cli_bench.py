@@ -95,6 +95,27 @@ if __name__ == "__main__":
             print(f"rank {rank}: {len(files)} files scored in {time.perf_counter() - t:.2f}s", file=sys.stderr, flush=True)
 
     EM.score_files = timed_score_files
+    if world > 1 and os.environ.get("OWC_CLI_TIMING"):           # where a multi-rank run spends the rest
+        _gather = dist.gather_object
+
+        def timed_gather(*a, **k):
+            t = time.perf_counter()
+            try:
+                return _gather(*a, **k)
+            finally:
+                print(f"rank {rank}: gather_object {time.perf_counter() - t:.3f}s", file=sys.stderr, flush=True)
+
+        dist.gather_object = timed_gather
+        _find = EM.find_input_files
+
+        def timed_find(*a, **k):
+            t = time.perf_counter()
+            try:
+                return _find(*a, **k)
+            finally:
+                print(f"rank {rank}: find_input_files {time.perf_counter() - t:.3f}s", file=sys.stderr, flush=True)
+
+        EM.find_input_files = timed_find
     for mode in modes:
         work = os.path.join(base, mode, "logs")
         argv = ["-i", work, "-m", "semantic_similarity", "--io", mode, "--jobs", "16", "--log-level", "WARNING"]
@@ -104,8 +125,11 @@ if __name__ == "__main__":
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(_io.StringIO()):
             results[mode] = EM.main(EM.build_parser().parse_args(argv))      # gathers on rank 0 when world > 1
+        t_main = time.perf_counter() - t0
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if os.environ.get("OWC_CLI_TIMING"):
+            print(f"rank {rank}: main {t_main:.3f}s, with final sync {dt:.3f}s", file=sys.stderr, flush=True)
         if rank == 0:
             out[mode] = {"seconds": dt, "rows_per_s": total / dt, "args": " ".join(argv[2:])}
     if rank == 0:
