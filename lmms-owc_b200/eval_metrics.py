@@ -337,6 +337,13 @@ def main(args: Namespace) -> dict:
         from . import text as _text
 
         _text.default_rank = local_rank
+        try:                                   # torch calls without a device argument stay on this rank's GPU
+            import torch
+
+            if torch.cuda.is_available():
+                torch.cuda.set_device(local_rank % torch.cuda.device_count())
+        except ImportError:  # pragma: no cover
+            pass
         os.environ.setdefault("OWC_TOKENIZER_THREADS", str(max(1, (os.cpu_count() or 1) // world)))   # share the host
         mine = split_files_balanced(input_files, world)[rank]
         log.info("Rank %d/%d scores %d of the files", rank, world, len(mine))

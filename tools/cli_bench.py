@@ -48,6 +48,7 @@ if __name__ == "__main__":
     # under torchrun: one process per GPU, files dealt to the ranks by eval_metrics.main; rank 0 writes the logs
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)      # torch.cuda.synchronize() below must not create a context on GPU 0 in every rank
     if world > 1:
         import torch.distributed as dist
 
@@ -84,6 +85,7 @@ if __name__ == "__main__":
                        f"{world} GPU(s), one process each",
            "rows": total, "n_gpus": world}
     results = {}
+    T0 = [time.perf_counter()]
     _score_files = EM.score_files
 
     def timed_score_files(files, *a, **k):          # per-rank view: own files only, before the gather
@@ -96,16 +98,22 @@ if __name__ == "__main__":
 
     EM.score_files = timed_score_files
     if world > 1 and os.environ.get("OWC_CLI_TIMING"):           # where a multi-rank run spends the rest
-        _gather = dist.gather_object
+        def timed(mod, name):
+            fn = getattr(mod, name)
 
-        def timed_gather(*a, **k):
-            t = time.perf_counter()
-            try:
-                return _gather(*a, **k)
-            finally:
-                print(f"rank {rank}: gather_object {time.perf_counter() - t:.3f}s", file=sys.stderr, flush=True)
+            def wrapper(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    print(f"rank {rank}: {name} {time.perf_counter() - t:.3f}s at {time.perf_counter() - T0[0]:.3f}s", file=sys.stderr, flush=True)
 
-        dist.gather_object = timed_gather
+            setattr(mod, name, wrapper)
+
+        for _name in ("_gather_outputs", "format_report", "split_files_balanced", "_dist_context"):
+            timed(EM, _name)
+        timed(torch.cuda, "manual_seed_all")
+        timed(torch, "manual_seed")
         _find = EM.find_input_files
 
         def timed_find(*a, **k):
@@ -123,6 +131,7 @@ if __name__ == "__main__":
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        T0[0] = t0
         with contextlib.redirect_stdout(_io.StringIO()):
             results[mode] = EM.main(EM.build_parser().parse_args(argv))      # gathers on rank 0 when world > 1
         t_main = time.perf_counter() - t0
