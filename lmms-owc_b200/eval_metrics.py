@@ -278,32 +278,6 @@ def _dist_context():
     return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
 
 
-_gather_calls = 0
-
-
-def _gather_outputs(dist, per_file: dict, rank: int, world: int):
-    """Per-rank ``{file: outputs}`` dicts on rank 0 (``None`` elsewhere). The few hundred bytes travel through the
-    process group's key-value store: a gloo ``gather_object`` whose senders finish early was measured at 0.35-1.0 s
-    on rank 0 (2 ranks) against 1 ms here. Falls back to the collective when the store is not reachable."""
-    global _gather_calls
-    import pickle
-
-    _gather_calls += 1
-    try:
-        from torch.distributed.distributed_c10d import _get_default_store
-
-        store = _get_default_store()
-    except Exception:  # pragma: no cover - private helper moved: use the collective
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(per_file, parts, dst=0)
-        return parts
-    key = f"owc_cli_outputs/{_gather_calls}/"
-    if rank != 0:
-        store.set(key + str(rank), pickle.dumps(per_file))
-        return None
-    return [per_file] + [pickle.loads(store.get(key + str(r))) for r in range(1, world)]
-
-
 def format_report(tasks_outputs: dict) -> str:
     """``eval_metrics.py:155-171``: one block per (task, metric), one ``{model:<29}: {value:.3f}`` line per model."""
     blocks = []
@@ -352,7 +326,8 @@ def main(args: Namespace) -> dict:
     if world > 1:
         import torch.distributed as dist
 
-        parts = _gather_outputs(dist, per_file, rank, world)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(per_file, parts, dst=0)          # a few floats per file; the data path has no collective
         if rank != 0:
             return {}
         per_file = {f: out for part in parts for f, out in part.items()}

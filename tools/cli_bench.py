@@ -110,7 +110,7 @@ if __name__ == "__main__":
 
             setattr(mod, name, wrapper)
 
-        for _name in ("_gather_outputs", "format_report", "split_files_balanced", "_dist_context"):
+        for _name in ("format_report", "split_files_balanced", "_dist_context"):
             timed(EM, _name)
         timed(torch.cuda, "manual_seed_all")
         timed(torch, "manual_seed")
