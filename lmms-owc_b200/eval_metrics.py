@@ -115,8 +115,8 @@ def _native_eligible(metric_names: list[str]) -> bool:
 
 
 def _load_items_native(input_file: str):
-    """``(raw bytes, items)`` with items already reduced to ``(ref[0], pred[-1])`` strings, or ``None`` when the
-    file needs the pandas path."""
+    """``(raw bytes, items)`` with the items as ``jsonl.PackedPairs`` (the ``ref[0]`` / ``pred[-1]`` strings of every
+    row in two packed columns), or ``None`` when the file needs the pandas path."""
     from . import jsonl
 
     with open(input_file, "rb") as f:
