@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OWC_ABI_VERSION 1
+#define OWC_ABI_VERSION 2
 
 typedef struct owc_ctx owc_ctx;
 typedef struct owc_encoder owc_encoder;
@@ -148,25 +148,16 @@ int32_t owc_score(owc_encoder* enc, const int32_t* ids, int32_t ids_space, const
                   int32_t precision, float* out_scores, int32_t* out_idx, float* out_paired,
                   float* out_embeds, int32_t out_space);
 
-/* Kernel-level entry points used by the parity tests and bench.py's roofline leg.
- * owc_debug_gemm: C[m,n] = A[m,kdim] . W[n,kdim]^T (+ bias[n]) in the given precision; all
- * pointers DEVICE fp32 (bf16 mode rounds operands to bf16 first, as the encoder does). tile_n
- * selects the tcgen05 column-tile width (128, 192 or 256; 0 = the encoder's default).            */
-int32_t owc_debug_gemm(owc_ctx* ctx, const float* a, const float* w, const float* bias, int32_t m,
-                       int32_t n, int32_t kdim, int32_t precision, int32_t tile_n, float* c);
-/* Debug: run the 1-CTA tcgen05 kernel once on an m x n x kdim problem (bf16 output + bias epilogue;
- * gelu != 0 adds the GELU) on zero-filled operands and return per-CTA clock64 stamps, 8 int64 per CTA
- * (grid = ceil(m/128) CTAs): [0] entry, [1] setup done, [2] first operands landed, [3] last MMA issued,
- * [4] first accumulator ready, [5] epilogue done, [6] all warps done, [7] globaltimer (ns) at entry.  */
-int32_t owc_debug_gemm_timeline(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int64_t* stamps,
-                                int32_t max_ctas);
-/* Debug: CUDA-event time of `iters` back-to-back launches of the same 1-CTA kernel (ms per launch). */
-int32_t owc_debug_gemm_loop(owc_ctx* ctx, int32_t m, int32_t n, int32_t kdim, int32_t gelu, int32_t iters,
-                            float* ms_per_launch);
-/* Time `iters` back-to-back launches of the fused similarity+top-k kernel alone on bf16 operands
- * already resident in device memory (CUDA events on the ctx stream); ms_per_launch out.          */
-int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, int32_t k, int32_t iters,
-                             float* ms_per_launch);
+/* The matching half of owc_score on its own, for prediction embeddings that are already in DEVICE memory (owc_encode with
+ * out_space = OWC_MEM_DEVICE): top-k of zp zc^T plus the paired score S[i, targets[i]] (_group.py:544). Splitting the
+ * call lets a multi-GPU host encode its prediction shard while the class embeddings are still in flight (broadcast /
+ * all-gather over NCCL) and wait for them only here.
+ *   zp fp32 [n, dim] DEVICE, zc fp32 [c, dim] DEVICE; targets int32 [n] in targets_space or NULL; outputs in out_space.
+ * A target outside [0, c) fails the call (at its synchronisation for device outputs) instead of reading out of bounds. */
+int32_t owc_match(owc_ctx* ctx, const float* zp, int64_t n, const float* zc, int32_t c, int32_t dim,
+                  const int32_t* targets, int32_t targets_space, int32_t k, int32_t precision, float* out_scores,
+                  int32_t* out_idx, float* out_paired, int32_t out_space);
+
 /* ---- host-side tokenisation (tokenisation stays on the host) --------------------
  * Replaces the AutoTokenizer call of _text.py:193-195 for ASCII rows: BERT normaliser + pre-tokeniser + WordPiece
  * + "[CLS] A [SEP]" (MPNet: "<s> A </s>") + truncation, multi-threaded, written straight into the packed layout
@@ -228,12 +219,6 @@ int32_t owc_jsonl_set_columns(const char* buf, size_t len, const char* const* na
  * renames it over the samples file, so a crash never leaves a truncated one.                                      */
 int32_t owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
                                 const double* values, int32_t n_cols, size_t n_rows, const char* out_path);
-
-/* Debug: timeline of the block-resident fused encoder kernel (enc_fused.cuh). When the ctx was created with
- * OWC_FUSED_DBG=1 in the environment, the first SIMT thread of CTA 0 records clock64 at: block start,
- * residual rows loaded, then per layer: attention block done, LayerNorm 1 done, feed-forward done,
- * LayerNorm 2 done. Copies the 2048 int64 debug words (stamps, phase sums, event traces) of the most recent launch to `stamps` (HOST).      */
-int32_t owc_debug_fused_stamps(owc_encoder* enc, int64_t* stamps);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,10 @@ KCATS = ("embed_ln", "gemm", "attn", "ln", "pool_l2", "sim_topk", "rescore", "mi
 _P = C.c_void_p
 _I32, _I64 = C.c_int32, C.c_int64
 
-# name -> (restype, argtypes); every symbol include/owc_b200.h declares
+ABI_VERSION = 2
+
+# name -> (restype, argtypes); every symbol include/owc_b200.h (product ABI) and include/owc_b200_debug.h (test /
+# measurement hooks) declare
 EXPORTS = {
     "owc_abi_version": (_I32, []),
     "owc_last_error": (C.c_char_p, []),
@@ -59,6 +62,7 @@ EXPORTS = {
     "owc_pair_dot": (_I32, [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "owc_sim_topk": (_I32, [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "owc_score": (_I32, [_P, _P, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32]),
+    "owc_match": (_I32, [_P, _P, _I64, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _I32]),
     "owc_debug_gemm": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "owc_debug_gemm_timeline": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32]),
     "owc_debug_gemm_loop": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
@@ -100,7 +104,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.owc_abi_version() != 1:
+        if handle.owc_abi_version() != ABI_VERSION:
             raise OwcError("libowc_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -10,13 +10,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <vector>
 
 #include "../../include/owc_b200.h"
+#include "../../include/owc_b200_debug.h"
 #include "attn_mma.cuh"
 #include "enc_fused.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_wide.cuh"
 #include "kernels.cuh"
 
 using namespace owc;
@@ -76,6 +79,9 @@ struct owc_ctx {
   int enc_wide = 1;        // 256-column tiles for wide encoders (env OWC_ENC_WIDE=0: kEncBN tiles everywhere)
   int fused_waves = 48;    // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES): one launch per 100 k-row step
   int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
+  int wide = 1;            // persistent CTA-pair GEMMs with deferred LayerNorm for H >= 768 (gemm_wide.cuh; env OWC_WIDE)
+  int wide_waves = 8;      // row-block pairs per cluster and chunk on that path (env OWC_WIDE_WAVES)
+  std::map<const void*, size_t> smem_attr;   // kernels whose dynamic shared-memory opt-in was set on THIS device
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -95,6 +101,10 @@ struct LayerW {
   CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;          // W maps, box = kEncBN rows (1-CTA kernel)
   CUtensorMap tm2_wqkv, tm2_wo, tm2_w1, tm2_w2;      // W maps, box = kEncBN/2 rows (CTA-pair kernel)
   CUtensorMap tmw_wqkv, tmw_wo, tmw_w1, tmw_w2;      // W maps, box = 128 rows (CTA-pair kernel, 256-column tiles; wide encoders)
+  // deferred-LayerNorm path (gemm_wide.cuh): gamma-folded bf16 copies of Wqkv / W1 and their epilogue vectors
+  const __nv_bfloat16 *fqkv = nullptr, *f1 = nullptr;
+  const float *c1q = nullptr, *c2q = nullptr, *c1f = nullptr, *c2f = nullptr;
+  CUtensorMap tmf_wqkv, tmf_w1;                      // box = 128 rows
 };
 
 struct owc_encoder {
@@ -116,6 +126,10 @@ struct owc_encoder {
   __nv_bfloat16 *fw_qkv = nullptr, *fw_o = nullptr, *fw_1 = nullptr, *fw_2 = nullptr;
   CUtensorMap tmf_qkv, tmf_o, tmf_1, tmf_2;
   bool wide = false;               // every GEMM width is a multiple of 256 (mpnet-base: 2304 / 768 / 3072): 256-column tiles
+  bool wide_ln = false;            // the deferred-LayerNorm path is set up (wide && ctx->wide)
+  __nv_bfloat16* wfold16 = nullptr;   // gamma-folded Wqkv | W1 of every layer
+  float* wfold32 = nullptr;           // c1q | c2q | c1f | c2f of every layer
+  float *st1 = nullptr, *st2 = nullptr;   // [cap][2] row (sum, sumsq) after the attention block / after the feed-forward block
   int fcap = 0;                    // tokens per fused launch
   float* fx = nullptr;             // [fcap + 128, H] fp32 residual stream of a fused chunk
   long long* fdbg = nullptr;       // [1024] timeline stamps + event traces
@@ -222,6 +236,19 @@ static int make_out_tmap(owc_ctx* c, CUtensorMap* m, const void* base, uint64_t 
   return 0;
 }
 
+// The dynamic shared-memory opt-in is a per-device (per-context) function attribute, and one process may hold contexts
+// on several GPUs: track it per owc_ctx, not in a process-wide static.
+template <typename F>
+static int ensure_smem_attr(owc_ctx* c, F* func, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  const void* key = reinterpret_cast<const void*>(func);
+  auto it = c->smem_attr.find(key);
+  if (it != c->smem_attr.end() && it->second >= bytes) return 0;
+  CU_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  c->smem_attr[key] = bytes;
+  return 0;
+}
+
 static int check_gemm_shape(const GemmArgs& g, int epi) {
   if (g.K % 64 != 0 || g.K <= 0) return fail("tcgen05 GEMM needs K %% 64 == 0 (K=%d)", g.K);
   if (epi == EPI_BIAS_RES_F32 && g.N % 32 != 0) return fail("residual epilogue needs N %% 32 == 0 (N=%d)", g.N);
@@ -232,11 +259,7 @@ template <int BN, int EPI, int KC, bool ARES>
 static int launch_gemm_tc_impl(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs g,
                                int splits, const CUtensorMap* td) {
   using Cfg = GemmCfg<BN, EPI, ARES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU_OK(cudaFuncSetAttribute(k_gemm_tc<BN, EPI, KC, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  OWC_TRY(ensure_smem_attr(c, k_gemm_tc<BN, EPI, KC, ARES>, Cfg::SMEM_BYTES));
   OWC_TRY(check_gemm_shape(g, EPI));
   const int tiles = (g.N + BN - 1) / BN;
   splits = std::max(1, std::min(splits, tiles));
@@ -280,11 +303,7 @@ template <int BN, int EPI, int KC, bool ARES>
 static int launch_gemm_tc2(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, GemmArgs g,
                            int splits) {
   using Cfg = Gemm2Cfg<BN, EPI, ARES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU_OK(cudaFuncSetAttribute(k_gemm_tc2<BN, EPI, KC, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  OWC_TRY(ensure_smem_attr(c, k_gemm_tc2<BN, EPI, KC, ARES>, Cfg::SMEM_BYTES));
   OWC_TRY(check_gemm_shape(g, EPI));
   if (ARES && g.K > kAresMaxK) return fail("resident-A GEMM needs K <= %d (K=%d)", kAresMaxK, g.K);
   const int tiles = (g.N + BN - 1) / BN;
@@ -329,6 +348,34 @@ static int launch_enc_gemm(owc_ctx* c, bool wide, const CUtensorMap& ta, const C
   if (wide && c->enc_wide && mode != 0)
     return launch_gemm_tc2<256, EPI, 1, false>(c, ta, tb_wide, tc, g, pick_splits(c, g.M, g.N, 256));
   return launch_gemm<kEncBN, EPI, 1>(c, ta, tb_full, tb_half, tc, g);
+}
+
+// Persistent CTA-pair contraction of the wide encoder path (gemm_wide.cuh). `tb` is the W map with a 128-row box.
+template <int EPI>
+static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
+                            WideArgs g) {
+  OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI>, WideCfg::SMEM_BYTES));
+  if (g.K % 64 != 0 || g.K <= 0 || g.N % 256 != 0 || g.N <= 0 || g.M <= 0) return fail("wide GEMM: bad shape %d x %d x %d", g.M, g.N, g.K);
+  const int clusters_max = std::max(1, c->sm_count / 2);
+  const int tiles = g.N / 256;
+  g.n_pairs = (g.M + 255) / 256;
+  int splits = g.n_pairs >= clusters_max ? 1 : std::min(tiles, (clusters_max + g.n_pairs - 1) / g.n_pairs);
+  g.tiles_per_item = (tiles + splits - 1) / splits;
+  g.splits = (tiles + g.tiles_per_item - 1) / g.tiles_per_item;
+  const int clusters = std::min(g.n_pairs * g.splits, clusters_max);
+  ProfScope prof(c, OWC_KCAT_GEMM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = WideCfg::SMEM_BYTES;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_OK(cudaLaunchKernelEx(&cfg, k_gemm_wide<EPI>, ta, tb, tc, td, g));
+  return check_launch(c, "k_gemm_wide");
 }
 
 template <int EPF>
@@ -390,6 +437,8 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* ew = getenv("OWC_ENC_WIDE")) c->enc_wide = atoi(ew) != 0;
   if (const char* fw = getenv("OWC_FUSED_WAVES")) c->fused_waves = std::max(1, std::min(64, atoi(fw)));
   if (const char* fd = getenv("OWC_FUSED_DBG")) c->fused_dbg = atoi(fd) != 0;
+  if (const char* wd = getenv("OWC_WIDE")) c->wide = atoi(wd) != 0;
+  if (const char* ww = getenv("OWC_WIDE_WAVES")) c->wide_waves = std::max(1, std::min(64, atoi(ww)));
   c->chunk_default = chunk_tokens <= 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
@@ -433,6 +482,7 @@ static int sync_and_check(owc_ctx* c) {
   CU_OK(cudaStreamSynchronize(c->stream));
   if (status != 0) {
     cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
+    if (status & 2) return fail("target / row index out of range for its table (status %d)", status);
     return fail("token id out of range for the embedding table (status %d)", status);
   }
   return 0;
@@ -506,7 +556,7 @@ extern "C" int32_t owc_encoder_destroy(owc_encoder* e) {
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
   void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32,
-                  e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg};
+                  e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg, e->wfold16, e->wfold32, e->st1, e->st2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -535,9 +585,12 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   e->arch = a;
   // one 128-row block per SM; wide encoders (CTA-pair GEMMs) run two waves per launch (measured on mpnet-base:
   // 129.1 ms per c3 step against 132.5 ms; more than two changes nothing)
-  e->cap = (c->chunk_default && a.hidden >= 768) ? 2 * c->chunk_tokens : c->chunk_tokens;
   const size_t h = a.hidden, I = a.inter;
   e->wide = h >= 768 && h % 256 == 0 && I % 256 == 0;
+  e->wide_ln = e->wide && c->wide;
+  e->cap = (c->chunk_default && a.hidden >= 768) ? 2 * c->chunk_tokens : c->chunk_tokens;
+  // the persistent kernels of the deferred-LayerNorm path amortise their launch over several waves of row-block pairs
+  if (c->chunk_default && e->wide_ln) e->cap = (c->sm_count / 2) * 256 * c->wide_waves;
 #define LOAD_FAIL(...) do { int _r = fail(__VA_ARGS__); owc_encoder_destroy(e); return _r; } while (0)
 #define LOAD_CU(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) LOAD_FAIL("%s failed: %s", #expr, cudaGetErrorString(_e)); } while (0)
   LOAD_CU(cudaMalloc(&e->w32, n_floats * sizeof(float)));
@@ -603,6 +656,39 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   if (make_out_tmap(c, &e->tmo_qkv, e->qkv, cap, 3 * h, true) || make_out_tmap(c, &e->tmo_f, e->f, cap, I, true) ||
       make_out_tmap(c, &e->tmo_y, e->y, cap, h, false) || make_out_tmap(c, &e->tmo_x, e->x, cap, h, false) ||
       make_out_tmap(c, &e->tmo_xb, e->xb, cap, h, true)) { owc_encoder_destroy(e); return 1; }
+  // ---- deferred-LayerNorm path of wide encoders (gemm_wide.cuh): gamma-folded Wqkv / W1 and their epilogue vectors ----
+  if (e->wide_ln) {
+    const size_t L = a.layers;
+    LOAD_CU(cudaMalloc(&e->wfold16, L * (3 * h * h + I * h) * sizeof(__nv_bfloat16)));
+    LOAD_CU(cudaMalloc(&e->wfold32, L * 2 * (3 * h + I) * sizeof(float)));
+    LOAD_CU(cudaMalloc(&e->st1, cap * 2 * sizeof(float)));
+    LOAD_CU(cudaMalloc(&e->st2, cap * 2 * sizeof(float)));
+    LOAD_CU(cudaMemsetAsync(e->st1, 0, cap * 2 * sizeof(float), c->stream));
+    LOAD_CU(cudaMemsetAsync(e->st2, 0, cap * 2 * sizeof(float), c->stream));
+    __nv_bfloat16* w16 = e->wfold16;
+    float* v32 = e->wfold32;
+    for (size_t l = 0; l < L; ++l) {
+      LayerW& Lw = e->layers[l];
+      // the LayerNorm in front of the QKV projection: the embedding LayerNorm for layer 0, the previous layer's output LayerNorm after
+      const float* g_in = l == 0 ? e->emb_g : e->layers[l - 1].ln2g;
+      const float* b_in = l == 0 ? e->emb_b : e->layers[l - 1].ln2b;
+      Lw.fqkv = w16; w16 += 3 * h * h;
+      Lw.f1 = w16; w16 += I * h;
+      Lw.c1q = v32; v32 += 3 * h;
+      Lw.c2q = v32; v32 += 3 * h;
+      Lw.c1f = v32; v32 += I;
+      Lw.c2f = v32; v32 += I;
+      k_fold_weight<<<static_cast<unsigned>((3 * h + 7) / 8), 256, 0, c->stream>>>(
+          Lw.wqkv32, g_in, b_in, Lw.bqkv, static_cast<int>(3 * h), static_cast<int>(h), const_cast<__nv_bfloat16*>(Lw.fqkv),
+          const_cast<float*>(Lw.c1q), const_cast<float*>(Lw.c2q));
+      if (check_launch(c, "k_fold_weight")) { owc_encoder_destroy(e); return 1; }
+      k_fold_weight<<<static_cast<unsigned>((I + 7) / 8), 256, 0, c->stream>>>(
+          Lw.w132, Lw.ln1g, Lw.ln1b, Lw.b1, static_cast<int>(I), static_cast<int>(h), const_cast<__nv_bfloat16*>(Lw.f1),
+          const_cast<float*>(Lw.c1f), const_cast<float*>(Lw.c2f));
+      if (check_launch(c, "k_fold_weight")) { owc_encoder_destroy(e); return 1; }
+      if (make_tmap(c, &Lw.tmf_wqkv, Lw.fqkv, 3 * h, h, 128) || make_tmap(c, &Lw.tmf_w1, Lw.f1, I, h, 128)) { owc_encoder_destroy(e); return 1; }
+    }
+  }
   // ---- block-resident fused encoder: MiniLM-width BERT only (enc_fused.cuh) ----
   e->fused_ok = a.kind == OWC_ARCH_BERT && a.hidden == fz::H && a.heads == fz::HEADS && a.inter % 128 == 0 && a.inter >= 128;
   if (e->fused_ok) {
@@ -652,11 +738,7 @@ static int launch_attn(owc_encoder* e, const AttnArgs& aa) {
   ProfScope prof(c, OWC_KCAT_ATTN);
 #define ATTN_LAUNCH(DD, WPP, KPL)                                                                         \
   do {                                                                                                    \
-    static size_t smem_set = 0;                                                                           \
-    if (smem > 48 * 1024 && smem > smem_set) {                                                            \
-      CU_OK(cudaFuncSetAttribute(k_attn<T, DD, WPP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      smem_set = smem;                                                                                    \
-    }                                                                                                     \
+    OWC_TRY(ensure_smem_attr(c, k_attn<T, DD, WPP, KPL>, smem));                                          \
     k_attn<T, DD, WPP, KPL><<<grid, 128, smem, c->stream>>>(aa);                                          \
   } while (0)
   if (D == 32) {
@@ -682,11 +764,7 @@ static int launch_attn_mma(owc_encoder* e, const AttnArgs& aa) {
 #define ATTN_MMA_LAUNCH(DD, TP)                                                                             \
   do {                                                                                                      \
     constexpr int smem = AttnWarpCfg<DD>::smem_bytes(TP);                                                   \
-    static bool attr_done = false;                                                                          \
-    if (smem > 48 * 1024 && !attr_done) {                                                                   \
-      CU_OK(cudaFuncSetAttribute(k_attn_mma<DD, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
-      attr_done = true;                                                                                     \
-    }                                                                                                       \
+    OWC_TRY(ensure_smem_attr(c, k_attn_mma<DD, TP>, smem));                                                 \
     const int per_sm = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));                             \
     const long long want = (pairs + 3) / 4;                                                                 \
     const unsigned grid = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(c->sm_count) * per_sm)); \
@@ -823,6 +901,68 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
   return 0;
 }
 
+// Wide encoders (H = 768) in bf16: persistent CTA-pair GEMMs with the LayerNorms deferred into their consumers
+// (gemm_wide.cuh). Per layer: QKV (fold) -> attention -> O-projection (+residual, statistics) -> FFN1 (fold + GELU)
+// -> FFN2 (+residual, statistics); e->x holds the PRE-LayerNorm sum y, e->xb its bf16 copy, st1 / st2 the row statistics.
+static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, int seq0, int n_seq, int tok0, int M,
+                             int max_t, float* z, __nv_bfloat16* zb) {
+  owc_ctx* c = e->ctx;
+  const owc_arch& a = e->arch;
+  const int H = a.hidden, I = a.inter;
+
+  EmbedArgs ea{};
+  ea.ids = d_ids; ea.cu = d_cu; ea.seq0 = seq0; ea.n_seq = n_seq; ea.tok0 = tok0;
+  ea.word = e->word; ea.pos = e->pos; ea.type0 = e->type0; ea.gamma = e->emb_g; ea.beta = e->emb_b;
+  ea.eps = a.ln_eps; ea.H = H; ea.vocab = a.vocab; ea.max_pos = a.max_pos;
+  ea.mpnet = a.kind == OWC_ARCH_MPNET; ea.pad_id = a.pad_id;
+  ea.x = e->x; ea.xb = e->xb; ea.status = c->d_status; ea.stats = e->st2;
+  {
+    ProfScope prof(c, OWC_KCAT_EMBED);
+    DISPATCH_NV(H, k_embed_ln<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(ea));
+  }
+  OWC_TRY(check_launch(c, "k_embed_ln"));
+
+  AttnArgs aa{};
+  aa.cu = d_cu; aa.seq0 = seq0; aa.n_seq = n_seq; aa.tok0 = tok0; aa.H = H; aa.heads = a.heads; aa.max_t = max_t;
+  aa.scale = 1.0f / sqrtf(static_cast<float>(H / a.heads));
+  aa.rel_lut = e->rel_lut; aa.max_pos = a.max_pos;
+  aa.qkv = e->qkv; aa.out = e->ao;
+
+  for (int l = 0; l < a.layers; ++l) {
+    const LayerW& L = e->layers[l];
+    const float* g_in = l == 0 ? e->emb_g : e->layers[l - 1].ln2g;
+    const float* b_in = l == 0 ? e->emb_b : e->layers[l - 1].ln2b;
+    WideArgs g{};
+    g.M = M; g.N = 3 * H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
+    g.c1 = L.c1q; g.c2 = L.c2q; g.stats_in = e->st2; g.stats_zero = e->st1;
+    OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g));
+    if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
+    else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
+    g = WideArgs{};
+    g.M = M; g.N = H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
+    g.bias = L.bo; g.y = e->x; g.stats_prev = e->st2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;
+    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_x, e->tmo_xb, g));
+    g = WideArgs{};
+    g.M = M; g.N = I; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
+    g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.stats_zero = e->st2;
+    OWC_TRY(launch_gemm_wide<WEPI_FOLD_GELU_BF16>(c, e->tm_xb, L.tmf_w1, e->tmo_f, e->tmo_f, g));
+    g = WideArgs{};
+    g.M = M; g.N = H; g.K = I; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
+    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
+    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g));
+  }
+  const LayerW& LL = e->layers[a.layers - 1];
+  {
+    ProfScope prof(c, OWC_KCAT_POOL);
+    DISPATCH_NV(H, k_pool_ln_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->x, e->st2, LL.ln2g, LL.ln2b, a.ln_eps, d_cu, seq0, n_seq,
+                                                                           tok0, H, z, zb));
+  }
+  OWC_TRY(check_launch(c, "k_pool_ln_l2"));
+  c->stats.tokens_encoded += M;
+  c->stats.sequences_encoded += n_seq;
+  return 0;
+}
+
 // Block-resident fused path (enc_fused.cuh): sequences are grouped greedily into 128-token row blocks of
 // whole sequences; each launch carries up to e->fcap tokens worth of blocks through every layer.
 // Per launch: k_embed_ln -> fx (fp32), k_encoder_fused (fx in place), k_pool_l2.
@@ -863,7 +1003,14 @@ static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t*
   fa.ln_eps = a.ln_eps;
   fa.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(H / a.heads));
   fa.dbg = c->fused_dbg ? e->fdbg : nullptr;
-  if (const char* ab = getenv("OWC_FUSED_ABLATE")) fa.ablate = atoi(ab);   // debug only: results are wrong when set
+  // role ablation (wrong results by construction) exists for tools/fused_ablate.py only: it needs OWC_DEBUG_HOOKS=1 as well,
+  // so a stray OWC_FUSED_ABLATE in a production environment cannot corrupt embeddings silently
+  if (const char* ab = getenv("OWC_FUSED_ABLATE")) {
+    const char* hooks = getenv("OWC_DEBUG_HOOKS");
+    if (atoi(ab) != 0 && !(hooks && atoi(hooks) != 0))
+      return fail("OWC_FUSED_ABLATE is set without OWC_DEBUG_HOOKS=1: refusing to run the ablated (wrong-result) kernel");
+    fa.ablate = atoi(ab);
+  }
 
   int b0 = 0;
   while (b0 < n_blk) {
@@ -941,6 +1088,12 @@ static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const i
       ++s1;
     }
     if (s1 == s0) return fail("internal: chunk capacity %d below one sequence", e->cap);
+    if (e->wide_ln && precision == OWC_PREC_BF16) {
+      OWC_TRY(encode_chunk_wide(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), s0, s1 - s0, cu[s0],
+                                cu[s1] - cu[s0], max_t, z, zb));
+      s0 = s1;
+      continue;
+    }
     OWC_TRY(encode_chunk(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), s0, s1 - s0, cu[s0],
                          cu[s1] - cu[s0], max_t, precision, z, zb));
     s0 = s1;
@@ -990,8 +1143,8 @@ extern "C" int32_t owc_pair_dot(owc_ctx* c, const float* a, int64_t na, const in
   }
   ProfScope prof(c, OWC_KCAT_RESCORE);
   k_pair_dot<<<static_cast<unsigned>((n + 7) / 8), 256, 0, c->stream>>>(
-      static_cast<const float*>(da), static_cast<const int32_t*>(dai), static_cast<const float*>(db),
-      static_cast<const int32_t*>(dbi), n, dim, dout);
+      static_cast<const float*>(da), static_cast<const int32_t*>(dai), na, static_cast<const float*>(db),
+      static_cast<const int32_t*>(dbi), nb, n, dim, dout, c->d_status);
   OWC_TRY(check_launch(c, "k_pair_dot"));
   if (space == OWC_MEM_HOST) {
     OWC_TRY(from_device(c, out, dout, static_cast<size_t>(n) * sizeof(float), OWC_MEM_HOST));
@@ -1052,7 +1205,8 @@ static int sim_topk_device(owc_ctx* c, const float* zp, const __nv_bfloat16* zpb
     const size_t smem = 4 * 2 * static_cast<size_t>(splits) * KC * sizeof(float);
     ProfScope prof(c, OWC_KCAT_RESCORE);
     k_rescore<<<static_cast<unsigned>((n + 3) / 4), 128, smem, c->stream>>>(zp, zc, n, dim, static_cast<const int*>(c->cand_i.p),
-                                                                            splits, KC, k, targets, d_scores, d_idx, d_paired);
+                                                                            splits, KC, k, targets, C, d_scores, d_idx, d_paired,
+                                                                            c->d_status);
     return check_launch(c, "k_rescore");
   }
   // check mode: materialise fp32 score rows in slabs, then top-k per row
@@ -1069,7 +1223,7 @@ static int sim_topk_device(owc_ctx* c, const float* zp, const __nv_bfloat16* zpb
   }
   if (targets && d_paired) {
     ProfScope prof(c, OWC_KCAT_RESCORE);
-    k_pair_dot<<<static_cast<unsigned>((n + 7) / 8), 256, 0, c->stream>>>(zc, targets, zp, nullptr, n, dim, d_paired);
+    k_pair_dot<<<static_cast<unsigned>((n + 7) / 8), 256, 0, c->stream>>>(zc, targets, C, zp, nullptr, n, n, dim, d_paired, c->d_status);
     OWC_TRY(check_launch(c, "k_pair_dot"));
   }
   return 0;
@@ -1161,6 +1315,50 @@ extern "C" int32_t owc_score(owc_encoder* e, const int32_t* ids, int32_t ids_spa
     OWC_TRY(from_device(c, out_idx, di, n * k * sizeof(int32_t), OWC_MEM_HOST));
     if (targets && out_paired) OWC_TRY(from_device(c, out_paired, dp, n * sizeof(float), OWC_MEM_HOST));
     if (out_embeds) OWC_TRY(from_device(c, out_embeds, z, n * H * sizeof(float), OWC_MEM_HOST));
+    return sync_and_check(c);
+  }
+  return 0;
+}
+
+// The matching half of owc_score on embeddings that already sit in device memory.
+extern "C" int32_t owc_match(owc_ctx* c, const float* zp, int64_t n, const float* zc, int32_t C, int32_t dim,
+                             const int32_t* targets, int32_t targets_space, int32_t k, int32_t precision, float* out_scores,
+                             int32_t* out_idx, float* out_paired, int32_t out_space) {
+  if (!c || !zp || !zc || !out_scores || !out_idx) return fail("owc_match: NULL argument");
+  if (n < 0 || C <= 0 || dim <= 0 || dim % 4 != 0) return fail("owc_match: bad shape");
+  if (n == 0) return 0;
+  CU_OK(cudaSetDevice(c->device));
+  const size_t nn = static_cast<size_t>(n);
+  const bool host_out = out_space == OWC_MEM_HOST;
+  const __nv_bfloat16 *zpb = nullptr, *zcb = nullptr;
+  if (precision == OWC_PREC_BF16) {
+    OWC_TRY(ensure(c, c->zpb, nn * dim * 2));
+    OWC_TRY(ensure(c, c->zcb, static_cast<size_t>(C) * dim * 2));
+    OWC_TRY(launch_convert(c, zp, static_cast<__nv_bfloat16*>(c->zpb.p), n * dim));
+    OWC_TRY(launch_convert(c, zc, static_cast<__nv_bfloat16*>(c->zcb.p), static_cast<long long>(C) * dim));
+    zpb = static_cast<const __nv_bfloat16*>(c->zpb.p);
+    zcb = static_cast<const __nv_bfloat16*>(c->zcb.p);
+  }
+  const void* d_targets = nullptr;
+  if (targets) OWC_TRY(to_device(c, c->targets, targets, nn * sizeof(int32_t), targets_space, &d_targets));
+  float *ds = out_scores, *dp = out_paired;
+  int32_t* di = out_idx;
+  if (host_out) {
+    OWC_TRY(ensure(c, c->out_s, nn * k * sizeof(float)));
+    OWC_TRY(ensure(c, c->out_i, nn * k * sizeof(int32_t)));
+    ds = static_cast<float*>(c->out_s.p);
+    di = static_cast<int32_t*>(c->out_i.p);
+    if (out_paired) {
+      OWC_TRY(ensure(c, c->out_p, nn * sizeof(float)));
+      dp = static_cast<float*>(c->out_p.p);
+    }
+  }
+  OWC_TRY(sim_topk_device(c, zp, zpb, n, zc, zcb, C, dim, k, precision, static_cast<const int32_t*>(d_targets), ds, di,
+                          (targets && out_paired) ? dp : nullptr));
+  if (host_out) {
+    OWC_TRY(from_device(c, out_scores, ds, nn * k * sizeof(float), OWC_MEM_HOST));
+    OWC_TRY(from_device(c, out_idx, di, nn * k * sizeof(int32_t), OWC_MEM_HOST));
+    if (targets && out_paired) OWC_TRY(from_device(c, out_paired, dp, nn * sizeof(float), OWC_MEM_HOST));
     return sync_and_check(c);
   }
   return 0;

@@ -74,6 +74,7 @@ struct EmbedArgs {
   float* x;                  // [chunk tokens, H] fp32 residual stream
   __nv_bfloat16* xb;         // bf16 operand copy, or nullptr in check mode
   int* status;               // bit 0: an id was out of range (clamped)
+  float* stats;              // wide path: [chunk tokens][2] row (sum, sumsq); x / xb then hold the UN-normalised sum
 };
 
 // One warp per sequence; tokens visited in order so MPNet's position id (running count of
@@ -125,6 +126,25 @@ __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
   };
   auto store = [&](int t, float4 (&x)[NV]) {
     const size_t row = static_cast<size_t>(t - a.tok0);
+    if (a.stats != nullptr) {
+      // deferred LayerNorm (wide path, gemm_wide.cuh): the un-normalised sum, its bf16 copy and the row statistics
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + 32 * i;
+        s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+        q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+        reinterpret_cast<float4*>(a.x + row * a.H)[c4] = x[i];
+        uint2 p;
+        p.x = pack_bf16x2(x[i].x, x[i].y);
+        p.y = pack_bf16x2(x[i].z, x[i].w);
+        reinterpret_cast<uint2*>(a.xb + row * a.H)[c4] = p;
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      if (lane == 0) reinterpret_cast<float2*>(a.stats)[row] = make_float2(s, q);
+      return;
+    }
     ln_row_store<NV>(x, lane, a.H, a.gamma, a.beta, a.eps, a.x + row * a.H, a.xb ? a.xb + row * a.H : nullptr);
   };
   int t = beg;
@@ -304,6 +324,63 @@ __global__ void __launch_bounds__(128) k_pool_l2(const float* __restrict__ x, co
   }
 }
 
+// Wide path (gemm_wide.cuh): the last layer leaves the PRE-LayerNorm sum y with its row statistics; the mean over a
+// sequence's tokens of LN(y_t) is gamma * mean_t((y_t - mu_t) * rstd_t) + beta, so the LayerNorm costs one FMA per
+// element on the way into the pooling sum. Then the same masked mean + L2 as k_pool_l2.
+template <int NV>
+__global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y, const float* __restrict__ stats,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float eps, const int32_t* __restrict__ cu, int seq0, int n_seq, int tok0,
+                                                    int H, float* __restrict__ z, __nv_bfloat16* __restrict__ zb) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_seq) return;
+  const int beg = cu[seq0 + s] - tok0, end = cu[seq0 + s + 1] - tok0;
+  const float inv_h = 1.0f / static_cast<float>(H);
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = beg; t < end; ++t) {
+    const float2 st = reinterpret_cast<const float2*>(stats)[t];
+    const float mu = st.x * inv_h;
+    const float ra = rsqrtf(fmaxf(st.y * inv_h - mu * mu, 0.f) + eps);
+    const float rb = -mu * ra;
+    const float4* r4 = reinterpret_cast<const float4*>(y + static_cast<size_t>(t) * H);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = r4[lane + 32 * i];
+      acc[i].x += fmaf(v.x, ra, rb); acc[i].y += fmaf(v.y, ra, rb); acc[i].z += fmaf(v.z, ra, rb); acc[i].w += fmaf(v.w, ra, rb);
+    }
+  }
+  const float n_tok = static_cast<float>(end - beg);
+  const float cnt = fmaxf(n_tok, 1e-9f);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    // sum_t LN(y_t) = gamma * sum_t yhat_t + n_tok * beta  (an empty sequence sums to zero -> 0/0 = NaN below, as the reference)
+    acc[i].x = fmaf(acc[i].x, g.x, n_tok * b.x) / cnt; acc[i].y = fmaf(acc[i].y, g.y, n_tok * b.y) / cnt;
+    acc[i].z = fmaf(acc[i].z, g.z, n_tok * b.z) / cnt; acc[i].w = fmaf(acc[i].w, g.w, n_tok * b.w) / cnt;
+    ss += (acc[i].x * acc[i].x + acc[i].y * acc[i].y) + (acc[i].z * acc[i].z + acc[i].w * acc[i].w);
+  }
+  const float nrm = sqrtf(warp_sum(ss));
+  const size_t row = static_cast<size_t>(seq0 + s) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 o = make_float4(acc[i].x / nrm, acc[i].y / nrm, acc[i].z / nrm, acc[i].w / nrm);
+    reinterpret_cast<float4*>(z + row)[c4] = o;
+    if (zb != nullptr) {
+      uint2 p;
+      p.x = pack_bf16x2(o.x, o.y);
+      p.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(zb + row)[c4] = p;
+    }
+  }
+}
+
 __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ b, int dim, int lane) {
   float acc = 0.f;
   const int n4 = dim >> 2;
@@ -319,14 +396,21 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const flo
 
 // out[i] = <a[a_index ? a_index[i] : i], b[b_index ? b_index[i] : i]>
 // (_group.py:541/544 torch.bmm on (N,1,D)x(N,D,1))
-__global__ void __launch_bounds__(256) k_pair_dot(const float* __restrict__ a, const int32_t* __restrict__ a_index,
-                                                  const float* __restrict__ b, const int32_t* __restrict__ b_index,
-                                                  long long n, int dim, float* __restrict__ out) {
+// An index outside its table is clamped and reported through `status` bit 1 (the call then fails at its next sync)
+// instead of reading out of bounds.
+__global__ void __launch_bounds__(256) k_pair_dot(const float* __restrict__ a, const int32_t* __restrict__ a_index, long long na,
+                                                  const float* __restrict__ b, const int32_t* __restrict__ b_index, long long nb,
+                                                  long long n, int dim, float* __restrict__ out, int* __restrict__ status) {
   const int lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
-  const long long ia = a_index ? a_index[i] : i;
-  const long long ib = b_index ? b_index[i] : i;
+  long long ia = a_index ? a_index[i] : i;
+  long long ib = b_index ? b_index[i] : i;
+  if (ia < 0 || ia >= na || ib < 0 || ib >= nb) {
+    if (lane == 0) atomicOr(status, 2);
+    ia = min(max(ia, 0LL), na - 1);
+    ib = min(max(ib, 0LL), nb - 1);
+  }
   const float s = warp_dot(a + ia * dim, b + ib * dim, dim, lane);
   if (lane == 0) out[i] = s;
 }
@@ -354,8 +438,9 @@ __device__ __forceinline__ bool better(float s1, int i1, float s2, int i2) {
 // paired target score. Warp per prediction row. cand_idx: [splits, n, KC]; entries < 0 are empty.
 __global__ void __launch_bounds__(128) k_rescore(const float* __restrict__ zp, const float* __restrict__ zc, long long n,
                                                  int dim, const int* __restrict__ cand_idx, int splits, int KC, int k,
-                                                 const int32_t* __restrict__ targets, float* __restrict__ out_scores,
-                                                 int32_t* __restrict__ out_idx, float* __restrict__ out_paired) {
+                                                 const int32_t* __restrict__ targets, int n_classes, float* __restrict__ out_scores,
+                                                 int32_t* __restrict__ out_idx, float* __restrict__ out_paired,
+                                                 int* __restrict__ status) {
   extern __shared__ float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncand = splits * KC;
@@ -386,7 +471,12 @@ __global__ void __launch_bounds__(128) k_rescore(const float* __restrict__ zp, c
     if (sub == 0 && c < ncand) { cs[c] = id >= 0 ? acc : -INFINITY; ci[c] = id; }
   }
   if (targets != nullptr && out_paired != nullptr) {
-    const float s = warp_dot(zp + r * dim, zc + static_cast<long long>(targets[r]) * dim, dim, lane);
+    int tg = targets[r];
+    if (tg < 0 || tg >= n_classes) {   // clamped and reported (status bit 1): never an out-of-bounds read
+      if (lane == 0) atomicOr(status, 2);
+      tg = min(max(tg, 0), n_classes - 1);
+    }
+    const float s = warp_dot(zp + r * dim, zc + static_cast<long long>(tg) * dim, dim, lane);
     if (lane == 0) out_paired[r] = s;
   }
   __syncwarp();

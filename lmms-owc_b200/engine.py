@@ -209,6 +209,62 @@ class Engine:
             self._leave()
         return scores, idx
 
+    @staticmethod
+    def _check_targets(targets, c: int) -> None:
+        """Host-side range check of numpy / host targets (device tensors are checked by the kernel, which clamps,
+        flags and fails the call at its next synchronisation)."""
+        if targets is None:
+            return
+        torch = _torch()
+        if isinstance(targets, torch.Tensor):
+            if targets.is_cuda or targets.numel() == 0:
+                return
+            lo, hi = int(targets.min()), int(targets.max())
+        else:
+            t = np.asarray(targets)
+            if t.size == 0:
+                return
+            lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= c:
+            raise IndexError(f"targets must lie in [0, {c}); got [{lo}, {hi}]")
+
+    def match(self, zp_device, zc_device, targets=None, k: int = 1, precision: str | None = None, out: str = "host") -> dict:
+        """Top-k of ``zp @ zc.T`` + paired target score on DEVICE-resident embeddings (``owc_match``): the second half of
+        :meth:`score`, so a multi-GPU caller can encode its shard while the class embeddings are still in flight."""
+        torch = _torch()
+        for t in (zp_device, zc_device):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("match needs contiguous fp32 CUDA tensors")
+        n, dim = zp_device.shape
+        c = zc_device.shape[0]
+        self._check_targets(targets, c)
+        p_t, sp_t, keep = None, _cabi.MEM_HOST, None
+        if targets is not None:
+            p_t, sp_t, keep = _as_arg(targets, np.int32, self.device)
+        res: dict = {}
+        if out == "host":
+            res["scores"] = np.empty((n, k), np.float32)
+            res["idx"] = np.empty((n, k), np.int32)
+            res["paired"] = np.empty(n, np.float32) if targets is not None else None
+            ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+            space = _cabi.MEM_HOST
+        else:
+            dev = self.torch_device
+            res["scores"] = torch.empty(n, k, dtype=torch.float32, device=dev)
+            res["idx"] = torch.empty(n, k, dtype=torch.int32, device=dev)
+            res["paired"] = torch.empty(n, dtype=torch.float32, device=dev) if targets is not None else None
+            ptr = lambda a: a.data_ptr() if a is not None else None  # noqa: E731
+            space = _cabi.MEM_DEVICE
+        if n == 0:
+            return res
+        self._enter()
+        _cabi.check(self._lib.owc_match(self._ctx, zp_device.data_ptr(), n, zc_device.data_ptr(), c, dim, p_t, sp_t, k,
+                                        self._prec(precision), ptr(res["scores"]), ptr(res["idx"]), ptr(res["paired"]), space))
+        if out != "host":
+            self._leave()
+        del keep
+        return res
+
     def score(self, ids, cu_seqlens, zc_device, targets=None, k: int = 1, precision: str | None = None,
               out: str = "host", want_embeds: bool = False) -> dict:
         """Whole path for one shard: encode + match + paired score. ``owc_score``."""
@@ -220,6 +276,7 @@ class Engine:
                 and zc_device.is_contiguous()):
             raise ValueError("zc_device must be a contiguous fp32 CUDA tensor [c, H]")
         c = zc_device.shape[0]
+        self._check_targets(targets, c)
         p_ids, sp_ids, keep1 = _as_arg(ids, np.int32, self.device)
         p_t, keep2 = None, None
         if targets is not None:

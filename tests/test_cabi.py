@@ -13,10 +13,19 @@ from owc_b200 import _cabi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "owc_b200.h"), encoding="utf-8").read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(owc_[a-z0-9_]+)\s*\(", text)))
+def _declared_symbols(headers=("owc_b200.h", "owc_b200_debug.h")):
+    names = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h), encoding="utf-8").read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(owc_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_product_header_carries_no_debug_hooks():
+    product = _declared_symbols(("owc_b200.h",))
+    assert not [n for n in product if "debug" in n or "bench" in n]
+    assert "owc_match" in product and "owc_score" in product
 
 
 def test_header_symbols_are_exported_and_bound():
@@ -30,7 +39,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_error_string():
     lib = _cabi.lib()
-    assert lib.owc_abi_version() == 1
+    assert lib.owc_abi_version() == _cabi.ABI_VERSION
     assert isinstance(lib.owc_last_error(), bytes)
 
 

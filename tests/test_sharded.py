@@ -30,6 +30,14 @@ def test_split_rows_balanced_properties():
             loads = [w[b0:b1].sum() for b0, b1 in blocks]
             assert max(loads) - min(loads) <= 2 * w.max()      # balanced by weight, not by row count
     assert sharded.split_rows_balanced([5, 5, 5, 5], 2) == [(0, 2), (2, 4)]
+    # a head start (rank 0's class-name encode) comes off that rank's share of the rows
+    w = np.full(1000, 10.0)
+    blocks = sharded.split_rows_balanced(w, 4, head_start=[400.0, 0, 0, 0])
+    loads = [w[b0:b1].sum() for b0, b1 in blocks]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 1000 and abs(loads[0] + 400 - loads[1]) <= 10 and abs(loads[1] - loads[3]) <= 10
+    assert sharded.split_rows_balanced(w, 2, head_start=[1e9, 0]) == [(0, 0), (0, 1000)]   # never negative
+    with pytest.raises(ValueError):
+        sharded.split_rows_balanced(w, 2, head_start=[1.0])
     with pytest.raises(ValueError):
         sharded.split_rows_balanced([1], 0)
 
@@ -75,6 +83,18 @@ class _OracleEngine:
             paired = (zp * zc[torch.from_numpy(np.asarray(targets)).long()]).sum(1)
         return {"scores": s.contiguous(), "idx": i.to(torch.int32).contiguous(), "paired": paired, "embeds": None}
 
+    def match(self, zp, zc, targets=None, k=1, precision=None, out="host"):
+        from oracle import encoder_ref
+
+        if zp.shape[0] == 0:
+            return {"scores": torch.zeros(0, k), "idx": torch.zeros(0, k, dtype=torch.int32),
+                    "paired": torch.zeros(0) if targets is not None else None}
+        s, i, _ = encoder_ref.sim_topk(zp, zc, k)
+        paired = None
+        if targets is not None:
+            paired = (zp * zc[torch.from_numpy(np.asarray(targets)).long()]).sum(1)
+        return {"scores": s.contiguous(), "idx": i.to(torch.int32).contiguous(), "paired": paired}
+
 
 def _small_setup():
     from owc_b200 import arch as A
@@ -100,12 +120,29 @@ def _worker(rank, world, port, queue):
         torch.set_num_threads(1)
         arch, sd, tok, classes, preds, targets = _small_setup()
         eng = _OracleEngine(arch, sd)
-        out = sharded.score_rows_sharded(eng, tok, classes, preds, targets, k=3)
+        out = sharded.score_rows_sharded(eng, tok, classes, preds, targets, k=3, head_start=40.0)
+        calls = eng.encode_calls
+        # vocabulary-scale class sets: every rank encodes an equal slice, one all_gather assembles [C, H] everywhere
+        cids, ccu = tok.encode_packed(classes)
+        zc_sliced = sharded.class_embeddings(eng, cids, ccu, shard_from=4).wait()
+        zc_full = _OracleEngine(arch, sd).encode(cids, ccu, out="device")
+        slice_err = float((zc_sliced - zc_full).abs().max())
+        slice_calls = eng.encode_calls - calls
+        # packed gather of unequal shards, without targets
+        counts = [5, 3]
+        g = sharded.ResultGatherer(counts, 2, "cpu", with_paired=False)
+        n = counts[rank]
+        recv = g.gather({"scores": torch.full((n, 2), float(rank)), "idx": torch.full((n, 2), 7 + rank, dtype=torch.int32)})
         if rank == 0:
-            queue.put({"scores": out["scores"], "idx": out["idx"], "paired": out["paired"], "calls": eng.encode_calls})
+            un = g.unpack(recv)
+            assert un["paired"] is None and un["scores"].shape == (8, 2)
+            assert (un["scores"][:5] == 0).all() and (un["scores"][5:] == 1).all()
+            assert (un["idx"][:5] == 7).all() and (un["idx"][5:] == 8).all()
+            queue.put({"scores": out["scores"], "idx": out["idx"], "paired": out["paired"], "calls": calls,
+                       "slice_err": slice_err, "slice_calls": slice_calls})
         else:
-            assert out is None
-            queue.put({"calls": eng.encode_calls, "rank": rank})
+            assert out is None and recv is None
+            queue.put({"calls": calls, "rank": rank, "slice_err": slice_err, "slice_calls": slice_calls})
     finally:
         dist.destroy_process_group()
 
@@ -136,9 +173,11 @@ def test_sharded_scoring_world2_matches_single_process():
     assert np.array_equal(r0["idx"], single["idx"])
     assert np.abs(r0["scores"] - single["scores"]).max() < 1e-6
     assert np.abs(r0["paired"] - single["paired"]).max() < 1e-6
-    # rank 0 encodes the class names (1) + its rows (1); rank 1 only probes + encodes its rows: the
-    # class embeddings reach it by broadcast, not by re-encoding
-    assert r0["calls"] == 2 and r1["calls"] == 2
+    # rank 0 encodes the class names (1) + its rows (1); rank 1 only encodes its rows: the class embeddings reach it
+    # by broadcast, not by re-encoding
+    assert r0["calls"] == 2 and r1["calls"] == 1
+    # sliced class encode: one encode call per rank (its slice), identical embeddings on both ranks
+    assert r0["slice_calls"] == 1 and r1["slice_calls"] == 1 and r0["slice_err"] < 1e-6 and r1["slice_err"] < 1e-6
 
 
 # ---- the CLI mirror under a multi-process launcher: files dealt to ranks, one report on rank 0 -------------------

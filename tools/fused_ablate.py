@@ -26,6 +26,7 @@ print(f"{rows} rows, {ntok} tokens, {flops/1e12:.3f} TFLOP of contractions", flu
 os.environ["OWC_FUSED"] = "1"
 e = Engine(arch, sd, device=0)
 for ab in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,4,8,3,7,15".split(","))]:
+    os.environ["OWC_DEBUG_HOOKS"] = "1"
     os.environ["OWC_FUSED_ABLATE"] = str(ab)
     for _ in range(2):
         e.encode(ids_d, cu, out="device")

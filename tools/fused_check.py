@@ -62,6 +62,7 @@ def main() -> None:
 
     e0 = make_engine(arch, sd, 0)
     z0 = e0.encode(ids, cu)
+    os.environ["OWC_DEBUG_HOOKS"] = "1"
     os.environ["OWC_FUSED_ABLATE"] = str(args.ablate)
     e1 = make_engine(arch, sd, 1, dbg=1)
     t0 = time.perf_counter()
