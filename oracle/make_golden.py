@@ -15,7 +15,10 @@ models (no network: no pretrained weights, no real vocab), and records what the 
 * ``tests/golden/minilm_caltech101.npz`` - MiniLM-L6 arch: strings, padded ids/mask of the first
   batch, embeddings from ``encode_sentence_bert``, paired scores from ``semantic_similarity``,
   MASS dict, concept-similarity rows (with the ``simple_concepts`` extractor standing in for spaCy);
-* ``tests/golden/mpnet_synth.npz`` - MPNet-base arch pushed through the same operator.
+* ``tests/golden/mpnet_synth.npz`` - MPNet-base arch pushed through the same operator;
+* ``tests/golden/mpnet_c3.npz`` - BASELINE config 3 in miniature (``--only-c3`` regenerates just this one): MPNet-base
+  arch, 1000 class names x 2048 predictions: paired scores from ``semantic_similarity`` and the top-5 / margins of
+  ``S = Zp Zc^T`` on the reference's own embeddings.
 
 Weights are NOT stored: both sides rebuild them with ``torch.manual_seed(1234)`` + HF default
 init (``build_model`` below); a few weight checksums are stored so a silently different RNG stream
@@ -159,7 +162,57 @@ def run_reference(arch, vocab, class_names, preds, targets, concept_preds):
     return out
 
 
+def run_reference_c3(n_classes: int = 1000, n_preds: int = 2048):
+    """BASELINE config 3 in miniature: the mpnet-base arch against 1000 class names. Records what the reference's own
+    operator + ``semantic_similarity`` return, and the top-5 / margins of ``S = Zp Zc^T`` on the reference's embeddings
+    (SURVEY.md 8c definition of the north-star extension). Embeddings are kept for the class names' first rows only:
+    the scores are what the parity test needs."""
+    import src.data.pipelines.text._text as T
+    from src.data.metrics import get_metric_info
+
+    arch = A.MPNET_BASE
+    vocab = synth.build_vocab("mpnet", arch.vocab)
+    words = synth.vocab_words(vocab)
+    cls = synth.make_class_names(n_classes, words, seed=SEED)
+    preds, targets = synth.make_predictions(n_preds, cls, words, seed=SEED)
+    model = build_model(arch)
+    T.sentence_bert_model = model
+    T.sentence_bert_processor = build_hf_tokenizer(arch, vocab)
+
+    def encode(texts, col):
+        parts = []
+        for s in range(0, len(texts), 1024):
+            e = T.encode_sentence_bert({col: texts[s:s + 1024]}, input_column=col)
+            parts.append(np.asarray(e[f"{col}_sentence_bert_embeds"], dtype=np.float32))
+        return np.concatenate(parts)
+
+    zc = encode(list(cls), "text")
+    zp = encode(list(preds), "prediction")
+    items = [(cls[t], [p]) for t, p in zip(targets, preds)]
+    mi = get_metric_info("semantic_similarity")
+    paired = np.asarray(mi.group_fn(mi.builder_fn(items), reduce="none"), dtype=np.float32)
+    s64 = torch.from_numpy(zp).double() @ torch.from_numpy(zc).double().T
+    s32 = torch.from_numpy(zp) @ torch.from_numpy(zc).T
+    order = torch.sort(s32, dim=1, descending=True, stable=True)
+    top64 = torch.sort(s64, dim=1, descending=True, stable=True).values
+    consistency = float((s32[torch.arange(len(preds)), torch.tensor(targets)] - torch.from_numpy(paired)).abs().max())
+    assert consistency < 1e-5, consistency     # S[i, target_i] == semantic_similarity(items, "none")[i]  (SURVEY 8c)
+    return {"n_classes": np.int32(n_classes), "n_preds": np.int32(n_preds), "seed": np.int32(SEED),
+            "targets": np.asarray(targets, dtype=np.int32), "paired_scores": paired,
+            "top5_scores": order.values[:, :5].numpy().astype(np.float32), "top5_idx": order.indices[:, :5].numpy().astype(np.int32),
+            "margin": (top64[:, 0] - top64[:, 1]).numpy().astype(np.float64),
+            "class_embeds_head": zc[:32], "pred_embeds_head": zp[:64],
+            "class_name_head": np.array(cls[:8]), "pred_head": np.array(preds[:8]),
+            "weight_checksums": weight_checksums(model)}
+
+
 def main() -> None:
+    if "--only-c3" in sys.argv:
+        install_reference_shims()
+        out = run_reference_c3()
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mpnet_c3.npz"), **out)
+        print("c3:", out["top5_scores"].shape, float(out["paired_scores"].mean()), "near-ties:", int((out["margin"] < 1e-3).sum()))
+        return
     names = extract_class_names()
     os.makedirs(os.path.join(ROOT, "lmms-owc_b200", "assets"), exist_ok=True)
     with open(os.path.join(ROOT, "lmms-owc_b200", "assets", "class_names.json"), "w", encoding="utf-8") as f:
@@ -192,6 +245,10 @@ def main() -> None:
     out = run_reference(A.MPNET_BASE, mvocab, mcls, mpreds, mtargets, None)
     np.savez_compressed(os.path.join(gold, "mpnet_synth.npz"), **out)
     print("mpnet:", out["pred_embeds"].shape, float(out["paired_mean"]))
+
+    out = run_reference_c3()
+    np.savez_compressed(os.path.join(gold, "mpnet_c3.npz"), **out)
+    print("c3:", out["top5_scores"].shape, float(out["paired_scores"].mean()))
 
 
 if __name__ == "__main__":

@@ -107,3 +107,30 @@ def test_mpnet_bucket_table_matches_reference_expression():
     want = encoder_ref.mpnet_bucket(rel)
     got = torch.tensor([mpnet_relative_bucket(int(r)) for r in rel])
     assert torch.equal(want, got)
+
+
+def test_oracle_matches_reference_c3_golden(mpnet):
+    """BASELINE config 3 in miniature (mpnet-base arch x 1000 class names), produced by the reference itself
+    (oracle/make_golden.py --only-c3): paired scores of its semantic_similarity and the top-5 of S on its embeddings.
+    A 256-row slice keeps the CPU suite short; the whole golden is held against the CUDA path in tests/test_gpu_configs.py."""
+    import os
+
+    from owc_b200 import synth
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpnet_c3.npz"), allow_pickle=False))
+    b = mpnet
+    assert np.abs(g["weight_checksums"] - b.gold["weight_checksums"]).max() < 1e-6       # same seeded weights as the other fixture
+    cls = synth.make_class_names(int(g["n_classes"]), b.words, seed=int(g["seed"]))
+    preds, targets = synth.make_predictions(int(g["n_preds"]), cls, b.words, seed=int(g["seed"]))
+    assert [str(x) for x in g["pred_head"]] == preds[:8] and np.array_equal(np.asarray(targets, np.int32), g["targets"])
+    n = 256
+    zc = encoder_ref.encode_strings(b.sd, b.arch, b.hf_tok, cls)
+    zp = encoder_ref.encode_strings(b.sd, b.arch, b.hf_tok, preds[:n])
+    assert np.abs(zc[:32].numpy() - g["class_embeds_head"]).max() < 2e-6
+    assert np.abs(zp[:64].numpy() - g["pred_embeds_head"]).max() < 2e-6
+    scores, idx, margin = encoder_ref.sim_topk(zp, zc, 5)
+    assert np.abs(scores.numpy() - g["top5_scores"][:n]).max() < 2e-6
+    clear = g["margin"][:n] >= 1e-5
+    assert np.array_equal(idx.numpy()[clear], g["top5_idx"][:n][clear].astype(np.int64))
+    paired = encoder_ref.paired_dot(zc[torch.from_numpy(g["targets"][:n]).long()], zp)
+    assert np.abs(paired.numpy() - g["paired_scores"][:n]).max() < 2e-6
