@@ -481,7 +481,8 @@ def measure_rows(name: str, rows: int, d: Dist, steps: int, warmup: int, flush, 
     kernel_flops = gemm_flops + (attn_flops if fused else 0.0)   # the fused kernel runs the attention inside the same launch
     achieved = kernel_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
-    total_ms = sum(v["ms"] for v in prof.values())
+    shapes = ("gemm_qkv", "gemm_o", "gemm_ffn1", "gemm_ffn2")     # breakdown of "gemm" on the wide path: not added to totals
+    total_ms = sum(v["ms"] for k, v in prof.items() if k not in shapes)
     n_launch = max(prof["gemm"]["launches"], 1)
     traffic, tinfo = None, {}
     tpath = os.path.join(ROOT, "profiles", "r02_wide_traffic.json" if wide else "r01_fused_traffic.json")
@@ -501,9 +502,9 @@ def measure_rows(name: str, rows: int, d: Dist, steps: int, warmup: int, flush, 
                 "algorithmic_flops_per_launch": kernel_flops / n_launch, "launches_per_step": prof["gemm"]["launches"],
                 "avg_launch_ms": gemm_ms / n_launch, "share_of_step": gemm_ms / total_ms if total_ms else None,
                 "whole_step_tflops": (gemm_flops + attn_flops + 2.0 * wl.n_rows * len(wl.classes) * arch.hidden) / (total_ms / 1e3) / 1e12 if total_ms else None,
-                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
-                "class_names": {"launches": sum(v["launches"] for v in prof_cls.values()),
-                                "ms": round(sum(v["ms"] for v in prof_cls.values()), 4), "tokens": int(wl.ccu[-1])}}
+                "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items() if k not in shapes or v["launches"]},
+                "class_names": {"launches": sum(v["launches"] for k, v in prof_cls.items() if k not in shapes),
+                                "ms": round(sum(v["ms"] for k, v in prof_cls.items() if k not in shapes), 4), "tokens": int(wl.ccu[-1])}}
     sim_ms = prof["sim_topk"]["ms"]
     sim_in_step = None
     if sim_ms > 0:

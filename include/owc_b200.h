@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OWC_ABI_VERSION 2
+#define OWC_ABI_VERSION 3
 
 typedef struct owc_ctx owc_ctx;
 typedef struct owc_encoder owc_encoder;
@@ -80,7 +80,12 @@ enum {
   OWC_KCAT_SIM = 5,      /* k_gemm_tc with the top-k epilogue */
   OWC_KCAT_RESCORE = 6,  /* k_rescore / k_topk_rows / k_pair_dot */
   OWC_KCAT_MISC = 7,     /* conversions */
-  OWC_KCAT_COUNT = 8
+  /* per-shape breakdown of the wide encoder's contractions (k_gemm_wide); each launch is ALSO counted in OWC_KCAT_GEMM */
+  OWC_KCAT_GEMM_QKV = 8,
+  OWC_KCAT_GEMM_O = 9,
+  OWC_KCAT_GEMM_FFN1 = 10,
+  OWC_KCAT_GEMM_FFN2 = 11,
+  OWC_KCAT_COUNT = 12
 };
 typedef struct owc_profile {
   double ms[OWC_KCAT_COUNT];         /* summed device time of the launches, CUDA events on the ctx stream */

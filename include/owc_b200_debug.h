@@ -37,6 +37,12 @@ int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, in
  * LayerNorm 2 done. Copies the 2048 int64 debug words (stamps, phase sums, event traces) of the most recent launch to `stamps` (HOST).      */
 int32_t owc_debug_fused_stamps(owc_encoder* enc, int64_t* stamps);
 
+/* Debug: cycle counters of the instrumented persistent GEMM (gemm_wide.cuh), available when the ctx was created with
+ * OWC_WIDE_DBG=1: 32 int64 = [epilogue kind 0..3][8] {0: MMA warp waiting for operands, 1: waiting for a free accumulator,
+ * 2: MMA warp total, 3: epilogue warp waiting for an accumulator, 4: epilogue warp total, 5: leader CTAs counted}, summed
+ * over launches since the last reset.                                                                              */
+int32_t owc_debug_wide_counters(owc_ctx* ctx, int64_t* out32, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

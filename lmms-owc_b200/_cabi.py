@@ -35,15 +35,16 @@ class OwcStats(C.Structure):
 
 
 class OwcProfile(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8)]
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12)]
 
 
-KCATS = ("embed_ln", "gemm", "attn", "ln", "pool_l2", "sim_topk", "rescore", "misc")
+KCATS = ("embed_ln", "gemm", "attn", "ln", "pool_l2", "sim_topk", "rescore", "misc", "gemm_qkv", "gemm_o", "gemm_ffn1",
+         "gemm_ffn2")   # the last four break "gemm" down by shape on the wide path (each launch is in both)
 
 _P = C.c_void_p
 _I32, _I64 = C.c_int32, C.c_int64
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); every symbol include/owc_b200.h (product ABI) and include/owc_b200_debug.h (test /
 # measurement hooks) declare
@@ -68,6 +69,7 @@ EXPORTS = {
     "owc_debug_gemm_loop": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_bench_sim_kernel": (_I32, [_P, _I64, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
     "owc_debug_fused_stamps": (_I32, [_P, _P]),
+    "owc_debug_wide_counters": (_I32, [_P, _P, _I32]),
     "owc_tokenizer_last_error": (C.c_char_p, []),
     "owc_tokenizer_create": (_I32, [_P, _P, _I32, _I32, _I32, C.POINTER(_P)]),
     "owc_tokenizer_destroy": (_I32, [_P]),

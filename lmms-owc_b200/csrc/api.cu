@@ -80,8 +80,11 @@ struct owc_ctx {
   int fused_waves = 48;    // row-block pairs per cluster and launch of the fused encoder (env OWC_FUSED_WAVES): one launch per 100 k-row step
   int fused_dbg = 0;       // record the fused kernel's timeline stamps (env OWC_FUSED_DBG)
   int wide = 1;            // persistent CTA-pair GEMMs with deferred LayerNorm for H >= 768 (gemm_wide.cuh; env OWC_WIDE)
+  int attn_grp = 1;        // short sequences share 16 x 16 attention tiles on the wide path (k_attn_grp; env OWC_ATTN_GRP)
+  int wide_deep = 1;       // FFN2 on the 5-stage / single-residual-buffer variant of the residual epilogue (env OWC_WIDE_DEEP)
   int wide_waves = 8;      // row-block pairs per cluster and chunk on that path (env OWC_WIDE_WAVES)
   std::map<const void*, size_t> smem_attr;   // kernels whose dynamic shared-memory opt-in was set on THIS device
+  long long* wide_dbg = nullptr;             // [32] cycle counters of the instrumented wide GEMM (env OWC_WIDE_DBG=1), else nullptr
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -91,7 +94,7 @@ struct owc_ctx {
   std::vector<int> prof_cats;
   size_t prof_used = 0;
   // per-call scratch (grown on demand, reused across calls)
-  Buf ids, cu, targets, zp, zpb, zcb, zc32, cand_s, cand_i, out_s, out_i, out_p, tmp_a, tmp_b, tmp_c, tmp_d, blk;
+  Buf ids, cu, targets, zp, zpb, zcb, zc32, cand_s, cand_i, out_s, out_i, out_p, tmp_a, tmp_b, tmp_c, tmp_d, blk, grp;
 };
 
 struct LayerW {
@@ -129,12 +132,13 @@ struct owc_encoder {
   bool wide_ln = false;            // the deferred-LayerNorm path is set up (wide && ctx->wide)
   __nv_bfloat16* wfold16 = nullptr;   // gamma-folded Wqkv | W1 of every layer
   float* wfold32 = nullptr;           // c1q | c2q | c1f | c2f of every layer
-  float *st1 = nullptr, *st2 = nullptr;   // [cap][2] row (sum, sumsq) after the attention block / after the feed-forward block
+  float *st1 = nullptr, *st2 = nullptr;   // [slots][cap][2] partial row (sum, sumsq) after the attention block / the feed-forward block
   int fcap = 0;                    // tokens per fused launch
   float* fx = nullptr;             // [fcap + 128, H] fp32 residual stream of a fused chunk
   long long* fdbg = nullptr;       // [1024] timeline stamps + event traces
 };
 
+constexpr int kWideStatSlots = 2 * 4;   // partial row statistics: (column split, chunk parity) slots; H <= 1024 = 4 tiles of 256
 constexpr int kEncBN = 192;   // divides 3H, H and I of both architectures (1152/384/1536, 2304/768/3072)
 
 // ------------------------------------------------------------------------------------------------
@@ -175,7 +179,7 @@ static int from_device(owc_ctx* c, void* dst, const void* src, size_t bytes, int
 struct ProfScope {
   owc_ctx* c;
   cudaEvent_t stop = nullptr;
-  ProfScope(owc_ctx* ctx, int cat) : c(ctx) {
+  ProfScope(owc_ctx* ctx, int cat, int cat2 = -1) : c(ctx) {
     if (!c->profiling) return;
     if (c->prof_used + 2 > c->prof_events.size()) {
       cudaEvent_t a, b;
@@ -186,7 +190,7 @@ struct ProfScope {
     cudaEventRecord(c->prof_events[c->prof_used], c->stream);
     stop = c->prof_events[c->prof_used + 1];
     c->prof_used += 2;
-    c->prof_cats.push_back(cat);
+    c->prof_cats.push_back(cat | ((cat2 < 0 ? 0xff : cat2) << 8));
   }
   ~ProfScope() {
     if (stop) cudaEventRecord(stop, c->stream);
@@ -351,30 +355,44 @@ static int launch_enc_gemm(owc_ctx* c, bool wide, const CUtensorMap& ta, const C
 }
 
 // Persistent CTA-pair contraction of the wide encoder path (gemm_wide.cuh). `tb` is the W map with a 128-row box.
+// column splits of the persistent kernel for an M-row problem with `tiles` 256-column tiles (1 once every cluster has a row-block pair)
+static int wide_splits(const owc_ctx* c, int M, int tiles) {
+  const int clusters_max = std::max(1, c->sm_count / 2);
+  const int n_pairs = (M + 255) / 256;
+  const int splits = n_pairs >= clusters_max ? 1 : std::min(tiles, (clusters_max + n_pairs - 1) / n_pairs);
+  const int tpi = (tiles + splits - 1) / splits;
+  return (tiles + tpi - 1) / tpi;
+}
+
 template <int EPI>
 static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
-                            WideArgs g) {
-  OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI>, WideCfg::SMEM_BYTES));
+                            WideArgs g, int shape_cat) {
+  OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI, false>, WideCfg<EPI>::SMEM_BYTES));
+  if (c->wide_dbg) OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI, true>, WideCfg<EPI>::SMEM_BYTES));
   if (g.K % 64 != 0 || g.K <= 0 || g.N % 256 != 0 || g.N <= 0 || g.M <= 0) return fail("wide GEMM: bad shape %d x %d x %d", g.M, g.N, g.K);
   const int clusters_max = std::max(1, c->sm_count / 2);
   const int tiles = g.N / 256;
   g.n_pairs = (g.M + 255) / 256;
-  int splits = g.n_pairs >= clusters_max ? 1 : std::min(tiles, (clusters_max + g.n_pairs - 1) / g.n_pairs);
-  g.tiles_per_item = (tiles + splits - 1) / splits;
-  g.splits = (tiles + g.tiles_per_item - 1) / g.tiles_per_item;
+  g.splits = wide_splits(c, g.M, tiles);
+  g.tiles_per_item = (tiles + g.splits - 1) / g.splits;
   const int clusters = std::min(g.n_pairs * g.splits, clusters_max);
-  ProfScope prof(c, OWC_KCAT_GEMM);
+  g.dbg = c->wide_dbg;
+  if (c->wide_dbg) {
+    if (const char* ex = getenv("OWC_WIDE_EXP")) g.exp = atoi(ex);   // instrumented build only (wrong results by construction)
+  }
+  ProfScope prof(c, OWC_KCAT_GEMM, shape_cat);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = WideCfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = WideCfg<EPI>::SMEM_BYTES;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CU_OK(cudaLaunchKernelEx(&cfg, k_gemm_wide<EPI>, ta, tb, tc, td, g));
+  if (c->wide_dbg) CU_OK(cudaLaunchKernelEx(&cfg, k_gemm_wide<EPI, true>, ta, tb, tc, td, g));
+  else CU_OK(cudaLaunchKernelEx(&cfg, k_gemm_wide<EPI, false>, ta, tb, tc, td, g));
   return check_launch(c, "k_gemm_wide");
 }
 
@@ -439,6 +457,9 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* fd = getenv("OWC_FUSED_DBG")) c->fused_dbg = atoi(fd) != 0;
   if (const char* wd = getenv("OWC_WIDE")) c->wide = atoi(wd) != 0;
   if (const char* ww = getenv("OWC_WIDE_WAVES")) c->wide_waves = std::max(1, std::min(64, atoi(ww)));
+  if (const char* ag = getenv("OWC_ATTN_GRP")) c->attn_grp = atoi(ag) != 0;
+  if (const char* wd2 = getenv("OWC_WIDE_DEEP")) c->wide_deep = atoi(wd2) != 0;
+  const bool want_wide_dbg = getenv("OWC_WIDE_DBG") && atoi(getenv("OWC_WIDE_DBG")) != 0;
   c->chunk_default = chunk_tokens <= 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
   if (stream) {
@@ -457,6 +478,10 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   c->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   if (cudaMalloc(&c->d_status, sizeof(int)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
   cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
+  if (want_wide_dbg) {
+    if (cudaMalloc(&c->wide_dbg, 32 * sizeof(long long)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
+    cudaMemsetAsync(c->wide_dbg, 0, 32 * sizeof(long long), c->stream);
+  }
   *out = c;
   return 0;
 }
@@ -466,10 +491,11 @@ extern "C" int32_t owc_ctx_destroy(owc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   Buf* bufs[] = {&c->ids, &c->cu, &c->targets, &c->zp, &c->zpb, &c->zcb, &c->zc32, &c->cand_s, &c->cand_i,
-                 &c->out_s, &c->out_i, &c->out_p, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->blk};
+                 &c->out_s, &c->out_i, &c->out_p, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->blk, &c->grp};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_status) cudaFree(c->d_status);
+  if (c->wide_dbg) cudaFree(c->wide_dbg);
   for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -519,8 +545,13 @@ extern "C" int32_t owc_ctx_profile_end(owc_ctx* c, owc_profile* out) {
   for (size_t i = 0; i < c->prof_cats.size(); ++i) {
     float ms = 0.f;
     CU_OK(cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]));
-    out->ms[c->prof_cats[i]] += ms;
-    out->launches[c->prof_cats[i]] += 1;
+    const int cat = c->prof_cats[i] & 0xff, cat2 = (c->prof_cats[i] >> 8) & 0xff;
+    out->ms[cat] += ms;
+    out->launches[cat] += 1;
+    if (cat2 != 0xff) {   // the per-shape breakdown of the wide encoder's contractions
+      out->ms[cat2] += ms;
+      out->launches[cat2] += 1;
+    }
   }
   c->prof_used = 0;
   c->prof_cats.clear();
@@ -661,10 +692,11 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
     const size_t L = a.layers;
     LOAD_CU(cudaMalloc(&e->wfold16, L * (3 * h * h + I * h) * sizeof(__nv_bfloat16)));
     LOAD_CU(cudaMalloc(&e->wfold32, L * 2 * (3 * h + I) * sizeof(float)));
-    LOAD_CU(cudaMalloc(&e->st1, cap * 2 * sizeof(float)));
-    LOAD_CU(cudaMalloc(&e->st2, cap * 2 * sizeof(float)));
-    LOAD_CU(cudaMemsetAsync(e->st1, 0, cap * 2 * sizeof(float), c->stream));
-    LOAD_CU(cudaMemsetAsync(e->st2, 0, cap * 2 * sizeof(float), c->stream));
+    const size_t stat_bytes = kWideStatSlots * cap * 2 * sizeof(float);
+    LOAD_CU(cudaMalloc(&e->st1, stat_bytes));
+    LOAD_CU(cudaMalloc(&e->st2, stat_bytes));
+    LOAD_CU(cudaMemsetAsync(e->st1, 0, stat_bytes, c->stream));
+    LOAD_CU(cudaMemsetAsync(e->st2, 0, stat_bytes, c->stream));
     __nv_bfloat16* w16 = e->wfold16;
     float* v32 = e->wfold32;
     for (size_t l = 0; l < L; ++l) {
@@ -793,6 +825,44 @@ static int launch_attn_mma(owc_encoder* e, const AttnArgs& aa) {
   return check_launch(c, "k_attn_mma");
 }
 
+// Short sequences grouped into shared 16 x 16 tiles (attn_mma.cuh: k_attn_grp). aa.grp / aa.n_grp describe the groups.
+static int launch_attn_grp(owc_encoder* e, const AttnArgs& aa) {
+  owc_ctx* c = e->ctx;
+  const int D = e->arch.hidden / e->arch.heads;
+  const long long units = static_cast<long long>(aa.n_grp) * aa.heads;
+  ProfScope prof(c, OWC_KCAT_ATTN);
+#define ATTN_GRP_LAUNCH(DD, TP)                                                                             \
+  do {                                                                                                      \
+    constexpr int smem = AttnWarpCfg<DD>::smem_bytes(TP);                                                   \
+    OWC_TRY(ensure_smem_attr(c, k_attn_grp<DD, TP>, smem));                                                 \
+    const int per_sm = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));                             \
+    const long long want = (units + 3) / 4;                                                                 \
+    const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(c->sm_count) * per_sm))); \
+    cudaLaunchConfig_t cfg{};                                                                               \
+    cfg.gridDim = dim3(grid);                                                                               \
+    cfg.blockDim = dim3(128);                                                                               \
+    cfg.dynamicSmemBytes = smem;                                                                            \
+    cfg.stream = c->stream;                                                                                 \
+    cudaLaunchAttribute attr[1];                                                                            \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+    attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;                                    \
+    cfg.attrs = attr;                                                                                       \
+    cfg.numAttrs = 1;                                                                                       \
+    CU_OK(cudaLaunchKernelEx(&cfg, k_attn_grp<DD, TP>, aa));                                                \
+  } while (0)
+  if (D == 32) {
+    if (aa.max_t <= 16) ATTN_GRP_LAUNCH(32, 16);
+    else if (aa.max_t <= 32) ATTN_GRP_LAUNCH(32, 32);
+    else ATTN_GRP_LAUNCH(32, 64);
+  } else {
+    if (aa.max_t <= 16) ATTN_GRP_LAUNCH(64, 16);
+    else if (aa.max_t <= 32) ATTN_GRP_LAUNCH(64, 32);
+    else ATTN_GRP_LAUNCH(64, 64);
+  }
+#undef ATTN_GRP_LAUNCH
+  return check_launch(c, "k_attn_grp");
+}
+
 static int ensure_f32_workspace(owc_encoder* e) {
   if (e->qkv32) return 0;
   const size_t cap = e->cap, h = e->arch.hidden, I = e->arch.inter;
@@ -904,8 +974,8 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
 // Wide encoders (H = 768) in bf16: persistent CTA-pair GEMMs with the LayerNorms deferred into their consumers
 // (gemm_wide.cuh). Per layer: QKV (fold) -> attention -> O-projection (+residual, statistics) -> FFN1 (fold + GELU)
 // -> FFN2 (+residual, statistics); e->x holds the PRE-LayerNorm sum y, e->xb its bf16 copy, st1 / st2 the row statistics.
-static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, int seq0, int n_seq, int tok0, int M,
-                             int max_t, float* z, __nv_bfloat16* zb) {
+static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* cu, int seq0, int n_seq,
+                             int tok0, int M, int max_t, float* z, __nv_bfloat16* zb) {
   owc_ctx* c = e->ctx;
   const owc_arch& a = e->arch;
   const int H = a.hidden, I = a.inter;
@@ -927,34 +997,60 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
   aa.scale = 1.0f / sqrtf(static_cast<float>(H / a.heads));
   aa.rel_lut = e->rel_lut; aa.max_pos = a.max_pos;
   aa.qkv = e->qkv; aa.out = e->ao;
+  if (max_t <= 64 && c->attn_grp) {
+    // attention groups: runs of consecutive sequences with at most 16 tokens together share one 16 x 16 tile; a longer
+    // sequence is a group of its own
+    std::vector<int32_t> grp;
+    grp.reserve(static_cast<size_t>(M) / 8 + 2);
+    grp.push_back(seq0);
+    int rows = 0;
+    for (int s = seq0; s < seq0 + n_seq; ++s) {
+      const int len = cu[s + 1] - cu[s];
+      if (rows > 0 && rows + len > 16) {
+        grp.push_back(s);
+        rows = 0;
+      }
+      rows += len;
+    }
+    grp.push_back(seq0 + n_seq);
+    const void* d_grp = nullptr;
+    OWC_TRY(to_device(c, c->grp, grp.data(), grp.size() * sizeof(int32_t), OWC_MEM_HOST, &d_grp));
+    aa.grp = static_cast<const int32_t*>(d_grp);
+    aa.n_grp = static_cast<int>(grp.size()) - 1;
+  }
 
+  const int res_slots = 2 * wide_splits(c, M, H / 256);   // slots the O-projection / FFN2 kernels of this chunk write
+  const long long stride = e->cap;
   for (int l = 0; l < a.layers; ++l) {
     const LayerW& L = e->layers[l];
     const float* g_in = l == 0 ? e->emb_g : e->layers[l - 1].ln2g;
     const float* b_in = l == 0 ? e->emb_b : e->layers[l - 1].ln2b;
+    const int slots2 = l == 0 ? 1 : res_slots;   // the embedding kernel writes whole-row statistics into slot 0
     WideArgs g{};
-    g.M = M; g.N = 3 * H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
-    g.c1 = L.c1q; g.c2 = L.c2q; g.stats_in = e->st2; g.stats_zero = e->st1;
-    OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g));
-    if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
+    g.M = M; g.N = 3 * H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
+    g.c1 = L.c1q; g.c2 = L.c2q; g.stats_in = e->st2; g.slots_in = slots2;
+    OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g, OWC_KCAT_GEMM_QKV));
+    if (aa.grp != nullptr) OWC_TRY(launch_attn_grp(e, aa));
+    else if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
     else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
     g = WideArgs{};
-    g.M = M; g.N = H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
-    g.bias = L.bo; g.y = e->x; g.stats_prev = e->st2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;
-    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_x, e->tmo_xb, g));
+    g.M = M; g.N = H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
+    g.bias = L.bo; g.y = e->x; g.stats_prev = e->st2; g.slots_in = slots2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;
+    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_O));
     g = WideArgs{};
-    g.M = M; g.N = I; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
-    g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.stats_zero = e->st2;
-    OWC_TRY(launch_gemm_wide<WEPI_FOLD_GELU_BF16>(c, e->tm_xb, L.tmf_w1, e->tmo_f, e->tmo_f, g));
+    g.M = M; g.N = I; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
+    g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.slots_in = res_slots;
+    OWC_TRY(launch_gemm_wide<WEPI_FOLD_GELU_BF16>(c, e->tm_xb, L.tmf_w1, e->tmo_f, e->tmo_f, g, OWC_KCAT_GEMM_FFN1));
     g = WideArgs{};
-    g.M = M; g.N = H; g.K = I; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps;
-    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
-    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g));
+    g.M = M; g.N = H; g.K = I; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
+    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.slots_in = res_slots; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
+    if (c->wide_deep) OWC_TRY(launch_gemm_wide<WEPI_RES_STATS_DEEP>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2));
+    else OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2));
   }
   const LayerW& LL = e->layers[a.layers - 1];
   {
     ProfScope prof(c, OWC_KCAT_POOL);
-    DISPATCH_NV(H, k_pool_ln_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->x, e->st2, LL.ln2g, LL.ln2b, a.ln_eps, d_cu, seq0, n_seq,
+    DISPATCH_NV(H, k_pool_ln_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->x, e->st2, res_slots, stride, LL.ln2g, LL.ln2b, a.ln_eps, d_cu, seq0, n_seq,
                                                                            tok0, H, z, zb));
   }
   OWC_TRY(check_launch(c, "k_pool_ln_l2"));
@@ -1089,7 +1185,7 @@ static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const i
     }
     if (s1 == s0) return fail("internal: chunk capacity %d below one sequence", e->cap);
     if (e->wide_ln && precision == OWC_PREC_BF16) {
-      OWC_TRY(encode_chunk_wide(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), s0, s1 - s0, cu[s0],
+      OWC_TRY(encode_chunk_wide(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), cu, s0, s1 - s0, cu[s0],
                                 cu[s1] - cu[s0], max_t, z, zb));
       s0 = s1;
       continue;
@@ -1498,6 +1594,16 @@ extern "C" int32_t owc_debug_fused_stamps(owc_encoder* e, int64_t* out64) {
   CU_OK(cudaSetDevice(e->ctx->device));
   CU_OK(cudaMemcpyAsync(out64, e->fdbg, 2048 * sizeof(long long), cudaMemcpyDeviceToHost, e->ctx->stream));
   CU_OK(cudaStreamSynchronize(e->ctx->stream));
+  return 0;
+}
+
+extern "C" int32_t owc_debug_wide_counters(owc_ctx* c, int64_t* out32, int32_t reset) {
+  if (!c || !out32) return fail("owc_debug_wide_counters: NULL argument");
+  if (!c->wide_dbg) return fail("the ctx was not created with OWC_WIDE_DBG=1");
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaMemcpyAsync(out32, c->wide_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  if (reset) CU_OK(cudaMemsetAsync(c->wide_dbg, 0, 32 * sizeof(long long), c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

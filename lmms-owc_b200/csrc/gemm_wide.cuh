@@ -21,7 +21,10 @@
 //        and finishes in its epilogue:   LN(y) W^T + b  =  rstd * (acc - mu * c1[n]) + c2[n],
 //        c1[n] = sum_k W'[n,k],  c2[n] = sum_k W[n,k] beta[k] + b[n]          (WEPI_FOLD_BF16 / WEPI_FOLD_GELU_BF16)
 //      * the GEMM that adds the residual normalises it while adding:   v = acc + bias + (y - mu) * rstd * gamma + beta,
-//        writes v over y (+ bf16 copy) and accumulates the new row statistics                      (WEPI_RES_STATS)
+//        writes v over y (+ bf16 copy) and leaves the new row statistics                           (WEPI_RES_STATS)
+//    Row statistics are kept as partial (sum, sumsq) pairs in SLOTS - one per (column split, chunk parity) of the
+//    producing kernel, each written with a plain store by exactly one thread - and summed in slot order by the
+//    consumer: no atomics, so the result does not depend on the order in which CTAs finish (bit-reproducible).
 //    The numerics are those of the straightforward scheme (tools/lnfold_emulate.py: max |d cos| 1.15e-3 vs 1.12e-3
 //    against the fp32 oracle; the bf16 rounding moves from LN(y) to y, whose row mean is small against its spread).
 //
@@ -37,7 +40,9 @@ namespace owc {
 enum : int {
   WEPI_FOLD_BF16 = 0,        // out bf16 = rstd_r * (acc - mu_r * c1[n]) + c2[n]
   WEPI_FOLD_GELU_BF16 = 1,   // out bf16 = gelu_erf(the same)
-  WEPI_RES_STATS = 2         // y = acc + bias[n] + LN_prev(y) in place (fp32) + bf16 copy; row (sum, sumsq) accumulated
+  WEPI_RES_STATS = 2,        // y = acc + bias[n] + LN_prev(y) in place (fp32) + bf16 copy; row (sum, sumsq) left in slots
+  WEPI_RES_STATS_DEEP = 3    // the same for long K (FFN2, K = 3072): a 5-stage operand ring paid for with a single residual
+                             // buffer per warp (the residual fetch is exposed, which a 24 k clk column tile hides easily)
 };
 
 struct WideArgs {
@@ -50,37 +55,50 @@ struct WideArgs {
   // WEPI_FOLD_*
   const float* c1;           // [N] row sums of the gamma-folded bf16 weights
   const float* c2;           // [N] W beta + bias
-  const float* stats_in;     // [M][2] (sum, sumsq) of the A operand's pre-LayerNorm rows
+  const float* stats_in;     // [slots_in][stat_stride][2] partial (sum, sumsq) of the A operand's pre-LayerNorm rows
   // WEPI_RES_STATS
   const float* bias;         // [N]
   float* y;                  // [M, N] fp32 residual stream, updated in place
-  const float* stats_prev;   // [M][2] statistics of y on entry
+  const float* stats_prev;   // partial statistics of y on entry (same layout, slots_in slots)
   const float* gamma_prev;   // [N] LayerNorm that turns y (on entry) into the residual
   const float* beta_prev;
-  float* stats_out;          // [M][2] accumulated atomically (zeroed by an earlier kernel of the layer)
+  float* stats_out;          // [2 * splits][stat_stride][2]: slot (split, chunk parity) written by this kernel
   // any epilogue
-  float* stats_zero;         // [M][2] or nullptr: zeroed here for a later kernel of the layer
+  int slots_in;              // partial-statistics slots of the incoming stream (1 after the embedding kernel)
+  long long stat_stride;     // rows between two slots of a statistics buffer
+  long long* dbg;            // DBG builds: [4 epilogue kinds][8] cycle counters, accumulated with atomics; else unused
+  int exp;                   // DBG builds only, WRONG results: bit 0 = load the A block for the first column tile of an item only
+                             // (what the ring would carry if A stayed on chip: is the kernel bound by L2 -> SM traffic?)
 };
 
+template <int EPI>
 struct WideCfg {
   static constexpr int BN = 256, BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;          // 32 KB
-  static constexpr int STAGES = 5;
-  static constexpr int STG_WARP = 6144;                           // per epilogue warp: 4 KB fp32 tile | 2 KB bf16 tile (or 2 x 2 KB bf16)
+  // per epilogue warp. fold: 2 x 2 KB bf16 output tiles. res: 2 x 4 KB fp32 tiles (the residual chunk lands here by TMA,
+  // is updated in place and TMA-stored back) + one 2 KB bf16 tile
+  static constexpr int RES_BUFS = EPI == WEPI_RES_STATS ? 2 : 1;
+  static constexpr int STG_WARP = (EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP) ? RES_BUFS * 4096 + 2048 : 2 * 2048;
+  static constexpr int STAGES = EPI == WEPI_RES_STATS ? 4 : 5;
   static constexpr int PARAM_BYTES = 2 * 3 * BN * 4;              // [tile parity][3 column vectors][BN]
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + kEpiWarps * STG_WARP + 512 + PARAM_BYTES;
   static_assert(SMEM_BYTES <= kSmemLimit, "shared memory budget");
 };
 
-template <int EPI>
+// DBG: the leader's MMA warp splits its time into waiting for operands (TMA-bound), waiting for a free accumulator
+// (epilogue-bound) and the rest (issue), and one epilogue warp its time waiting for accumulators; summed over CTAs into
+// g.dbg[EPI * 8 + {0: ring wait, 1: accumulator wait, 2: MMA warp total, 3: epilogue tfull wait, 4: epilogue total, 5: CTAs}].
+template <int EPI, bool DBG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const WideArgs g) {
-  using Cfg = WideCfg;
+  using Cfg = WideCfg<EPI>;
   constexpr int BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
-  constexpr bool RES = EPI == WEPI_RES_STATS;
+  constexpr bool RES = EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP;
+  constexpr int RB = Cfg::RES_BUFS;             // res: fp32 residual / output buffers per epilogue warp
+  constexpr int BBUF = Cfg::RES_BUFS * 4096;    // res: offset of the warp's bf16 output tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -91,6 +109,7 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);   // [kEpiWarps][2] res: residual chunk landed in the warp's fp32 buffer
   float* param_s = reinterpret_cast<float*>(tail + 512);   // [2][3][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -110,6 +129,9 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if constexpr (RES) tma_prefetch_desc(&tmD);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * kEpiWarps); }
+    if constexpr (RES) {
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -137,8 +159,9 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
             const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            if (leader) mbar_expect_tx(&full[stage], 2u * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
+            const bool skip_a = DBG && (g.exp & 1) && tile != tile0;
+            if (leader) mbar_expect_tx(&full[stage], skip_a ? 2u * Cfg::BH_BYTES : 2u * Cfg::STAGE_BYTES);
+            if (!skip_a) tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
             tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, bar, kb * BK, tile * BN + static_cast<int>(rank) * (BN / 2));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -153,16 +176,23 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       uint32_t t = 0;   // accumulator tiles issued so far (across items)
+      long long w_ring = 0, w_acc = 0, t_begin = 0;
+      if constexpr (DBG) t_begin = clock64();
       for (int it = cluster_id; it < n_items; it += n_clusters) {
         const int sp = it % g.splits;
         const int tile0 = sp * g.tiles_per_item, tile1 = min(tile0 + g.tiles_per_item, tiles_total);
         for (int tile = tile0; tile < tile1; ++tile, ++t) {
           const uint32_t buf = t & 1u;
+          long long c0 = 0;
+          if constexpr (DBG) c0 = clock64();
           mbar_wait(&tempty[buf], ((t >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
+          if constexpr (DBG) w_acc += clock64() - c0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
+            if constexpr (DBG) c0 = clock64();
             mbar_wait(&full[stage], phase);
+            if constexpr (DBG) w_ring += clock64() - c0;
             tc_fence_after();
             const uint32_t a_lo = tiles_lo + static_cast<uint32_t>(stage * (Cfg::STAGE_BYTES >> 4));
             if (elect_one_sync()) {
@@ -176,6 +206,14 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
         }
       }
+      if constexpr (DBG) {
+        if (lane == 0 && g.dbg != nullptr) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 0), static_cast<unsigned long long>(w_ring));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 1), static_cast<unsigned long long>(w_acc));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 2), static_cast<unsigned long long>(clock64() - t_begin));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 5), 1ull);
+        }
+      }
     }
   } else {
     // ---------------- epilogue (warps 2..9 of both CTAs, each CTA on its own 128 rows) ----------------
@@ -186,6 +224,9 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stg = stg_all + (warp - 2) * Cfg::STG_WARP;
     uint32_t t = 0;
     uint32_t store_count = 0;
+    uint32_t res_n = 0;   // res: residual chunks fetched / consumed so far by this warp (buffer = parity, barrier phase = bit 1)
+    long long w_tfull = 0, e_begin = 0;
+    if constexpr (DBG) e_begin = clock64();
     for (int it = cluster_id; it < n_items; it += n_clusters) {
       const int bp = it / g.splits, sp = it - bp * g.splits;
       const int m0 = bp * 2 * BM + static_cast<int>(rank) * BM;
@@ -194,18 +235,21 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool live = row < g.M;
       const int tile0 = sp * g.tiles_per_item, tile1 = min(tile0 + g.tiles_per_item, tiles_total);
       // per-row LayerNorm of the incoming stream: x = y * ra + rb
-      float ra = 0.f, rb = 0.f;
+      float ra = 0.f, rb_ = 0.f;
       {
-        const float* st = RES ? g.stats_prev : g.stats_in;
+        const float2* st = reinterpret_cast<const float2*>(RES ? g.stats_prev : g.stats_in);
         if (live) {
-          const float2 s2 = __ldg(reinterpret_cast<const float2*>(st) + row);
+          float2 s2 = __ldg(st + row);
+          for (int sl = 1; sl < g.slots_in; ++sl) {   // fixed slot order: bit-reproducible
+            const float2 p = __ldg(st + sl * g.stat_stride + row);
+            s2.x += p.x;
+            s2.y += p.y;
+          }
           const float mu = s2.x * g.inv_h;
           ra = rsqrtf(fmaxf(s2.y * g.inv_h - mu * mu, 0.f) + g.ln_eps);
-          rb = -mu * ra;
+          rb_ = -mu * ra;
         }
       }
-      if (g.stats_zero != nullptr && live && sp == 0 && half == 0)
-        reinterpret_cast<float2*>(g.stats_zero)[row] = make_float2(0.f, 0.f);
       float sum = 0.f, sq = 0.f;
       for (int tile = tile0; tile < tile1; ++tile, ++t) {
         const uint32_t buf = t & 1u;
@@ -221,24 +265,30 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             p0[BN + et] = __ldg(g.c2 + n);
           }
         }
-        // residual chunk of the first own column chunk, fetched before the accumulator is ready
-        float4 res[8];
-        auto fetch_res = [&](int n0) {
-          if constexpr (RES) {
-            if (live) {
-              const float4* r4 = reinterpret_cast<const float4*>(g.y + static_cast<size_t>(row) * g.N + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) res[j] = r4[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
+        // res: the residual chunk (32 rows x 32 fp32 of y) is brought in by TMA - coalesced, no LSU wavefronts - into one of
+        // the warp's two fp32 buffers, one chunk ahead; the thread updates its row in place and the buffer is TMA-stored back
+        // over y. (Row-per-thread global loads cost 32 LSU wavefronts per instruction: 8 warps x 4 chunks x 256 wavefronts per
+        // column tile exceeded the 6.1 k clk the O-projection's MMAs take and held that kernel at 0.46 PFLOP/s.)
+        auto fetch_res = [&](int n0) {   // lane 0; the buffer's previous TMA store has finished reading it (see below)
+          uint64_t* rb = &rbar[(warp - 2) * 2 + (res_n % RB)];
+          mbar_expect_tx(rb, 4096u);
+          tma_load_2d(stg + (res_n % RB) * 4096, &tmC, rb, n0, row0);
         };
-        fetch_res(tile * BN + half * 32);
+        if constexpr (RES) {
+          if (tile == tile0) {
+            if (lane == 0) {
+              bulk_wait_group_read<0>();   // the previous item's stores have read both buffers
+              fetch_res(tile * BN + half * 32);
+            }
+            __syncwarp();
+          }
+        }
         named_bar_sync(1, kEpiThreads);       // column parameters of this tile staged (the previous use of this
                                               // parity was two tiles ago: every warp has passed that tile's barrier)
+        long long c0 = 0;
+        if constexpr (DBG) c0 = clock64();
         mbar_wait(&tfull[buf], (t >> 1) & 1u);
+        if constexpr (DBG) w_tfull += clock64() - c0;
         tc_fence_after();
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
         uint32_t v[2][32];
@@ -252,43 +302,58 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t (&vc)[32] = v[cw & 1];
           float f[32];
           if constexpr (RES) {
-            float4 cur[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cur[j] = res[j];
-            if (cw + 1 < NCW) fetch_res(n0 + 64);   // next own chunk's residual flies under this chunk's math
+            uint8_t* fbuf = stg + (res_n % RB) * 4096;
+            uint64_t* rb = &rbar[(warp - 2) * 2 + (res_n % RB)];
+            const uint32_t rpar = (res_n / RB) & 1u;
+            ++res_n;
+            // next chunk of this item (same tile, or the first chunk of the next tile)
+            const bool more = cw + 1 < NCW || tile + 1 < tile1;
+            const int n_next = cw + 1 < NCW ? n0 + 64 : (tile + 1) * BN + half * 32;
+            if (lane == 0) {
+              bulk_wait_group_read<0>();   // the other buffer's last store (one chunk ago) and the bf16 tile's have read them
+              if (RB == 2 && more) fetch_res(n_next);   // two buffers: one chunk ahead, under this chunk's arithmetic
+            }
+            __syncwarp();
+            mbar_wait(rb, rpar);
+            uint8_t* rowp = fbuf + lane * 128;
+            const int sw = lane & 7;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+              float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4));   // SWIZZLE_128B, as TMA wrote it
+              const float4 r = *cell;
               const float4 b = *reinterpret_cast<const float4*>(p0 + c * 32 + 4 * j);
               const float4 gm = *reinterpret_cast<const float4*>(p0 + BN + c * 32 + 4 * j);
               const float4 bt = *reinterpret_cast<const float4*>(p0 + 2 * BN + c * 32 + 4 * j);
-              const float x0 = __uint_as_float(vc[4 * j + 0]) + b.x + fmaf(fmaf(cur[j].x, ra, rb), gm.x, bt.x);
-              const float x1 = __uint_as_float(vc[4 * j + 1]) + b.y + fmaf(fmaf(cur[j].y, ra, rb), gm.y, bt.y);
-              const float x2 = __uint_as_float(vc[4 * j + 2]) + b.z + fmaf(fmaf(cur[j].z, ra, rb), gm.z, bt.z);
-              const float x3 = __uint_as_float(vc[4 * j + 3]) + b.w + fmaf(fmaf(cur[j].w, ra, rb), gm.w, bt.w);
+              const float x0 = __uint_as_float(vc[4 * j + 0]) + b.x + fmaf(fmaf(r.x, ra, rb_), gm.x, bt.x);
+              const float x1 = __uint_as_float(vc[4 * j + 1]) + b.y + fmaf(fmaf(r.y, ra, rb_), gm.y, bt.y);
+              const float x2 = __uint_as_float(vc[4 * j + 2]) + b.z + fmaf(fmaf(r.z, ra, rb_), gm.z, bt.z);
+              const float x3 = __uint_as_float(vc[4 * j + 3]) + b.w + fmaf(fmaf(r.w, ra, rb_), gm.w, bt.w);
               sum += (x0 + x1) + (x2 + x3);
               sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+              *cell = make_float4(x0, x1, x2, x3);
               f[4 * j + 0] = x0; f[4 * j + 1] = x1; f[4 * j + 2] = x2; f[4 * j + 3] = x3;
             }
-            if (lane == 0) bulk_wait_group_read<0>();   // the stores that last used the staging buffers have read them
-            __syncwarp();
-            stage_chunk<EPI_BIAS_F32>(stg, lane, f);
-            stage_chunk<EPI_BIAS_BF16>(stg + 4096, lane, f);
+            stage_chunk<EPI_BIAS_BF16>(stg + BBUF, lane, f);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, stg, n0, row0);
-              tma_store_2d(&tmD, stg + 4096, n0, row0);
+              tma_store_2d(&tmC, fbuf, n0, row0);
+              tma_store_2d(&tmD, stg + BBUF, n0, row0);
               bulk_commit_group();
+              if (RB == 1 && more) {        // one buffer: the next chunk can only come in once this store has read it
+                bulk_wait_group_read<0>();
+                fetch_res(n_next);
+              }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 k1 = *reinterpret_cast<const float4*>(p0 + c * 32 + 4 * j);
               const float4 k2 = *reinterpret_cast<const float4*>(p0 + BN + c * 32 + 4 * j);
-              f[4 * j + 0] = fmaf(__uint_as_float(vc[4 * j + 0]), ra, fmaf(rb, k1.x, k2.x));
-              f[4 * j + 1] = fmaf(__uint_as_float(vc[4 * j + 1]), ra, fmaf(rb, k1.y, k2.y));
-              f[4 * j + 2] = fmaf(__uint_as_float(vc[4 * j + 2]), ra, fmaf(rb, k1.z, k2.z));
-              f[4 * j + 3] = fmaf(__uint_as_float(vc[4 * j + 3]), ra, fmaf(rb, k1.w, k2.w));
+              f[4 * j + 0] = fmaf(__uint_as_float(vc[4 * j + 0]), ra, fmaf(rb_, k1.x, k2.x));
+              f[4 * j + 1] = fmaf(__uint_as_float(vc[4 * j + 1]), ra, fmaf(rb_, k1.y, k2.y));
+              f[4 * j + 2] = fmaf(__uint_as_float(vc[4 * j + 2]), ra, fmaf(rb_, k1.z, k2.z));
+              f[4 * j + 3] = fmaf(__uint_as_float(vc[4 * j + 3]), ra, fmaf(rb_, k1.w, k2.w));
             }
             if constexpr (EPI == WEPI_FOLD_GELU_BF16) {
 #pragma unroll
@@ -312,13 +377,17 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
       }
       if constexpr (RES) {
-        if (live) {
-          atomicAdd(g.stats_out + 2 * static_cast<size_t>(row), sum);
-          atomicAdd(g.stats_out + 2 * static_cast<size_t>(row) + 1, sq);
-        }
+        if (live)   // this thread is the only writer of slot (split, chunk parity) of its row
+          reinterpret_cast<float2*>(g.stats_out)[(2 * sp + half) * g.stat_stride + row] = make_float2(sum, sq);
       }
     }
     if (lane == 0) bulk_wait_group<0>();   // staged tiles fully written before the CTA retires
+    if constexpr (DBG) {
+      if (warp == 2 && lane == 0 && leader && g.dbg != nullptr) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 3), static_cast<unsigned long long>(w_tfull));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + EPI * 8 + 4), static_cast<unsigned long long>(clock64() - e_begin));
+      }
+    }
   }
 
   tc_fence_before();

@@ -192,6 +192,8 @@ struct AttnArgs {
   float scale;               // head_dim^-0.5
   const float* rel_lut;      // MPNet: [heads, 2*max_pos-1] bias by (k - q); nullptr for BERT
   int max_pos;
+  const int32_t* grp;        // k_attn_grp: [n_grp + 1] absolute index of the first sequence of each group (device)
+  int n_grp;
 };
 
 // softmax(q k^T * scale (+ rel bias)) v for one (sequence, head) per group of WPP warps.
@@ -328,8 +330,9 @@ __global__ void __launch_bounds__(128) k_pool_l2(const float* __restrict__ x, co
 // sequence's tokens of LN(y_t) is gamma * mean_t((y_t - mu_t) * rstd_t) + beta, so the LayerNorm costs one FMA per
 // element on the way into the pooling sum. Then the same masked mean + L2 as k_pool_l2.
 template <int NV>
-__global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y, const float* __restrict__ stats,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y, const float* __restrict__ stats, int slots,
+                                                    long long stat_stride, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta,
                                                     float eps, const int32_t* __restrict__ cu, int seq0, int n_seq, int tok0,
                                                     int H, float* __restrict__ z, __nv_bfloat16* __restrict__ zb) {
   const int lane = threadIdx.x & 31;
@@ -341,7 +344,12 @@ __global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y,
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = beg; t < end; ++t) {
-    const float2 st = reinterpret_cast<const float2*>(stats)[t];
+    float2 st = reinterpret_cast<const float2*>(stats)[t];
+    for (int sl = 1; sl < slots; ++sl) {   // partial statistics, summed in slot order (gemm_wide.cuh)
+      const float2 p = reinterpret_cast<const float2*>(stats)[sl * stat_stride + t];
+      st.x += p.x;
+      st.y += p.y;
+    }
     const float mu = st.x * inv_h;
     const float ra = rsqrtf(fmaxf(st.y * inv_h - mu * mu, 0.f) + eps);
     const float rb = -mu * ra;

@@ -323,6 +323,12 @@ class Engine:
         self._leave()
         return out
 
+    def wide_counters(self, reset: bool = True) -> np.ndarray:
+        """Cycle counters of the instrumented wide GEMM (``OWC_WIDE_DBG=1``): ``[4, 8]`` int64, see owc_b200_debug.h."""
+        out = np.zeros(32, dtype=np.int64)
+        _cabi.check(self._lib.owc_debug_wide_counters(self._ctx, out.ctypes.data, int(reset)))
+        return out.reshape(4, 8)
+
     def bench_sim_kernel(self, n: int, c: int, dim: int, k: int, iters: int) -> float:
         ms = C.c_float(0.0)
         _cabi.check(self._lib.owc_bench_sim_kernel(self._ctx, n, c, dim, k, iters, C.byref(ms)))

@@ -83,10 +83,12 @@ def test_c3_wide_path_equals_per_gemm_path(mpnet, c3, monkeypatch):
         zp = plain.encode(ids, cu)
         assert np.isfinite(zw).all() and np.abs(np.linalg.norm(zw, axis=1) - 1).max() < 1e-5
         assert np.abs(zw - zp).max() < 2e-3
-        assert np.abs(zw - zs).max() < 1e-5       # row statistics are accumulated with atomics: order may differ in the last bit
+        # another chunking regroups the fp32 partial row statistics (column splits), and a last-bit change there flips
+        # bf16 roundings downstream: same tolerance as against the other path, not bit-identity
+        assert np.abs(zw - zs).max() < 2e-3
         assert n_launch <= 2 + 5 * mpnet.arch.layers          # embed + 12 x (QKV, attention, O, FFN1, FFN2) + pool: one chunk
-        z2 = wide.encode(ids, cu)
-        assert np.abs(z2 - zw).max() < 1e-5
+        assert np.array_equal(wide.encode(ids, cu), zw)       # no atomics anywhere: run-to-run bit-identical
+        assert np.array_equal(small.encode(ids, cu), zs)
     finally:
         wide.close()
         small.close()
@@ -107,7 +109,7 @@ def test_c3_full_size_properties(mpnet, eng_mpnet, c3):
     assert (np.diff(res["scores"], axis=1) <= 0).all()
     assert (res["scores"][:, 0] >= res["paired"] - 1e-6).all()
     hit = res["idx"][:, 0] == t
-    assert hit.sum() > 1000 and np.abs(res["scores"][hit, 0] - res["paired"][hit]).max() < 1e-6
+    assert hit.sum() > 50 and np.abs(res["scores"][hit, 0] - res["paired"][hit]).max() < 1e-6   # targets are uniform-random: ~0.1 % hits
     perm = np.random.default_rng(1).permutation(len(preds))[:4000]
     ids2, cu2 = tok.encode_packed([preds[i] for i in perm])
     res2 = eng.score(ids2, cu2, zc, targets=t[perm], k=5)

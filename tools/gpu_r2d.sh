@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2d_tests.log; echo "tests rc=$?"; tail -15 gpurun_out/r2d_tests.log
+timeout 600 python tools/wide_probe.py 100000 8 > gpurun_out/r2d_probe.log 2>&1; echo "probe rc=$?"; cat gpurun_out/r2d_probe.log
+OWC_ATTN_GRP=0 timeout 600 python tools/wide_probe.py 100000 8 2>&1 | head -1
