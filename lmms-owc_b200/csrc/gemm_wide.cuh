@@ -67,6 +67,8 @@ struct WideArgs {
   int slots_in;              // partial-statistics slots of the incoming stream (1 after the embedding kernel)
   long long stat_stride;     // rows between two slots of a statistics buffer
   long long* dbg;            // DBG builds: [4 epilogue kinds][8] cycle counters, accumulated with atomics; else unused
+  int rotate;                // cluster c walks the column tiles of its items starting at tile (c mod tiles): at any moment the
+                             // clusters stream DIFFERENT weight tiles instead of all hitting the same L2 lines in lockstep
   int exp;                   // DBG builds only, WRONG results: bit 0 = load the A block for the first column tile of an item only
                              // (what the ring would carry if A stayed on chip: is the kernel bound by L2 -> SM traffic?)
 };
@@ -154,12 +156,14 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int bp = it / g.splits, sp = it - bp * g.splits;
         const int m0 = bp * 2 * BM + static_cast<int>(rank) * BM;
         const int tile0 = sp * g.tiles_per_item, tile1 = min(tile0 + g.tiles_per_item, tiles_total);
-        for (int tile = tile0; tile < tile1; ++tile) {
+        const int nt = tile1 - tile0, rot = g.rotate ? cluster_id % nt : 0;
+        for (int j = 0; j < nt; ++j) {
+          const int tile = tile0 + (j + rot) % nt;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
             const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            const bool skip_a = DBG && (g.exp & 1) && tile != tile0;
+            const bool skip_a = DBG && (g.exp & 1) && j != 0;
             if (leader) mbar_expect_tx(&full[stage], skip_a ? 2u * Cfg::BH_BYTES : 2u * Cfg::STAGE_BYTES);
             if (!skip_a) tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
             tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, bar, kb * BK, tile * BN + static_cast<int>(rank) * (BN / 2));
@@ -181,7 +185,7 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int it = cluster_id; it < n_items; it += n_clusters) {
         const int sp = it % g.splits;
         const int tile0 = sp * g.tiles_per_item, tile1 = min(tile0 + g.tiles_per_item, tiles_total);
-        for (int tile = tile0; tile < tile1; ++tile, ++t) {
+        for (int j = tile0; j < tile1; ++j, ++t) {   // the tile order (rotation) only matters to the producer and the epilogue
           const uint32_t buf = t & 1u;
           long long c0 = 0;
           if constexpr (DBG) c0 = clock64();
@@ -251,7 +255,10 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       float sum = 0.f, sq = 0.f;
-      for (int tile = tile0; tile < tile1; ++tile, ++t) {
+      const int nt = tile1 - tile0, rot = g.rotate ? cluster_id % nt : 0;
+      for (int j = 0; j < nt; ++j, ++t) {
+        const int tile = tile0 + (j + rot) % nt;
+        const int tile_next = tile0 + (j + 1 + rot) % nt;
         const uint32_t buf = t & 1u;
         float* p0 = param_s + buf * 3 * BN;   // fold: c1 | c2     res: bias | gamma | beta
         {
@@ -275,7 +282,7 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tma_load_2d(stg + (res_n % RB) * 4096, &tmC, rb, n0, row0);
         };
         if constexpr (RES) {
-          if (tile == tile0) {
+          if (j == 0) {
             if (lane == 0) {
               bulk_wait_group_read<0>();   // the previous item's stores have read both buffers
               fetch_res(tile * BN + half * 32);
@@ -307,8 +314,8 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t rpar = (res_n / RB) & 1u;
             ++res_n;
             // next chunk of this item (same tile, or the first chunk of the next tile)
-            const bool more = cw + 1 < NCW || tile + 1 < tile1;
-            const int n_next = cw + 1 < NCW ? n0 + 64 : (tile + 1) * BN + half * 32;
+            const bool more = cw + 1 < NCW || j + 1 < nt;
+            const int n_next = cw + 1 < NCW ? n0 + 64 : tile_next * BN + half * 32;
             if (lane == 0) {
               bulk_wait_group_read<0>();   // the other buffer's last store (one chunk ago) and the bf16 tile's have read them
               if (RB == 2 && more) fetch_res(n_next);   // two buffers: one chunk ahead, under this chunk's arithmetic
