@@ -196,6 +196,7 @@ int32_t owc_tokenize_packed(const owc_tokenizer* tok, const char* text_bytes, co
                              eval_metrics.py:66-68 decides once per file on the first row ([[...], ...])            */
 #define OWC_JSONL_FLOAT 0 /* written as pandas writes doubles: "%.10f", trailing zeros trimmed, NaN/inf -> null    */
 #define OWC_JSONL_INT 1
+#define OWC_JSONL_RAW 2   /* a JSON fragment per row, written verbatim (list-valued columns of the concept metric)       */
 const char* owc_jsonl_last_error(void);
 int32_t owc_jsonl_count_rows(const char* buf, size_t len, size_t* n_rows);
 /* One string per row from top-level member `key`, JSON escapes decoded to UTF-8, each followed by one NUL byte, into
@@ -224,6 +225,17 @@ int32_t owc_jsonl_set_columns(const char* buf, size_t len, const char* const* na
  * renames it over the samples file, so a crash never leaves a truncated one.                                      */
 int32_t owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
                                 const double* values, int32_t n_cols, size_t n_rows, const char* out_path);
+/* The same with OWC_JSONL_RAW columns: raws[i] (NULL for numeric columns) holds n_rows JSON fragments, each followed by
+ * one NUL byte, written verbatim as the value of names[i] - the list-valued `last_resp_concepts` /
+ * `last_resp_concepts_similarities` columns the reference writes for concept_semantic_similarity (eval_metrics.py:93-104). */
+int32_t owc_jsonl_write_columns_raw(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                                    const double* values, const char* const* raws, int32_t n_cols, size_t n_rows,
+                                    const char* out_path);
+/* The raw JSON text of top-level member `key` of every row, each followed by one NUL byte, into out (cap >= len + rows
+ * suffices): how the CLI reads a list-valued column such as pre-extracted `prediction_concepts`.
+ * OWC_JSONL_UNSUPPORTED when a row lacks the member.                                                                  */
+int32_t owc_jsonl_extract_raw(const char* buf, size_t len, const char* key, char* out, size_t out_cap, size_t* out_len,
+                              size_t* n_rows);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,10 @@ EXPORTS = {
                                        C.POINTER(C.c_size_t)]),
     "owc_jsonl_write_columns": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(_I32), _P, _I32,
                                        C.c_size_t, C.c_char_p]),
+    "owc_jsonl_write_columns_raw": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(_I32), _P,
+                                           C.POINTER(C.c_char_p), _I32, C.c_size_t, C.c_char_p]),
+    "owc_jsonl_extract_raw": (_I32, [C.c_char_p, C.c_size_t, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_size_t)]),
     "owc_blob_unique": (_I32, [_P, C.c_size_t, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_size_t),
                                C.POINTER(C.c_size_t)]),
     "owc_jsonl_has_members": (_I32, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), _I32, C.POINTER(_I32)]),

@@ -116,6 +116,10 @@ inline void put_utf8(std::string& out, uint32_t cp) {
 bool decode_string(const char* p, const char* q, std::string& out, size_t line) {
     ++p;
     --q;
+    // A raw control byte inside a string is not JSON (pandas / json.loads raise on it), and a raw NUL would split the
+    // row in the NUL-separated blob: such a file is handed to the pandas path, which reports it like the reference does.
+    for (const char* c = p; c < q; ++c)
+        if ((unsigned char)*c < 0x20) return false;
     while (p < q) {
         const char* b = (const char*)memchr(p, '\\', (size_t)(q - p));
         if (!b) {
@@ -174,7 +178,10 @@ void walk_members(const char* p, const char* e, size_t line, F&& f) {
     ++p;
     const char* lead = p;
     p = skip_ws(p, e);
-    if (p < e && *p == '}') return;
+    if (p < e && *p == '}') {
+        if (skip_ws(p + 1, e) != e) fail(line, "trailing data after the object");
+        return;
+    }
     for (;;) {
         p = skip_ws(p, e);
         if (p >= e || *p != '"') fail(line, "member name expected");
@@ -193,7 +200,10 @@ void walk_members(const char* p, const char* e, size_t line, F&& f) {
         if (!last && *p != ',') fail(line, "',' or '}' expected");
         m.sep_e = last ? m.val_e : p + 1;
         f(m, m.key_b + 1, (size_t)(key_e - m.key_b - 2));
-        if (last) return;
+        if (last) {
+            if (skip_ws(p + 1, e) != e) fail(line, "trailing data after the object");   // `{...} junk`: pandas raises too
+            return;
+        }
         ++p;
         lead = p;
     }
@@ -302,11 +312,20 @@ inline void put_double(std::string& out, double v) {
 
 // Copies every row with its other members byte for byte, drops members named in names[] and appends
 // names[i]:values[i * n_rows + row]; hands the text to `sink` whenever `flush_at` bytes have accumulated and at the end.
+// OWC_JSONL_RAW columns take their per-row text (a JSON fragment, written verbatim) from raws[i]: n_rows fragments, each
+// followed by one NUL byte; values[] is ignored for them.
 template <class Sink>
 void render_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds, const double* values,
-                    int n_cols, size_t n_rows, size_t flush_at, Sink&& sink) {
+                    const char* const* raws, int n_cols, size_t n_rows, size_t flush_at, Sink&& sink) {
     std::vector<size_t> nl((size_t)n_cols);
     for (int i = 0; i < n_cols; ++i) nl[(size_t)i] = strlen(names[i]);
+    std::vector<const char*> raw_pos((size_t)n_cols, nullptr);
+    for (int i = 0; i < n_cols; ++i) {
+        if (kinds[i] == OWC_JSONL_RAW) {
+            if (!raws || !raws[i]) throw Fail{"jsonl: raw column without text"};
+            raw_pos[(size_t)i] = raws[i];
+        }
+    }
     std::string dst;
     dst.reserve(flush_at == ~size_t(0) ? len + n_rows * 32 * (size_t)(n_cols + 1) : flush_at + (size_t(1) << 16));
     size_t rows = 0;
@@ -338,9 +357,16 @@ void render_columns(const char* buf, size_t len, const char* const* names, const
             dst.push_back('"');
             dst.append(names[i], nl[(size_t)i]);
             dst += "\":";
-            const double v = values[(size_t)i * n_rows + rows];
-            if (kinds[i] == OWC_JSONL_INT && std::isfinite(v)) dst += std::to_string((long long)v);
-            else put_double(dst, v);
+            if (kinds[i] == OWC_JSONL_RAW) {
+                const char* frag = raw_pos[(size_t)i];
+                const size_t fl = strlen(frag);
+                dst.append(frag, fl);
+                raw_pos[(size_t)i] = frag + fl + 1;
+            } else {
+                const double v = values[(size_t)i * n_rows + rows];
+                if (kinds[i] == OWC_JSONL_INT && std::isfinite(v)) dst += std::to_string((long long)v);
+                else put_double(dst, v);
+            }
             any = true;
         }
         dst += "}\n";
@@ -548,7 +574,7 @@ int owc_jsonl_set_columns(const char* buf, size_t len, const char* const* names,
                           size_t* out_len) {
     return guarded([&] {
         size_t used = 0;
-        render_columns(buf, len, names, kinds, values, n_cols, n_rows, ~size_t(0), [&](const std::string& chunk) {
+        render_columns(buf, len, names, kinds, values, nullptr, n_cols, n_rows, ~size_t(0), [&](const std::string& chunk) {
             if (used + chunk.size() > out_cap) throw Fail{"jsonl: output buffer too small"};
             memcpy(out + used, chunk.data(), chunk.size());
             used += chunk.size();
@@ -558,13 +584,13 @@ int owc_jsonl_set_columns(const char* buf, size_t len, const char* const* names,
     });
 }
 
-int owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
-                            const double* values, int n_cols, size_t n_rows, const char* out_path) {
+static int write_columns_impl(const char* buf, size_t len, const char* const* names, const int32_t* kinds, const double* values,
+                              const char* const* raws, int n_cols, size_t n_rows, const char* out_path) {
     return guarded([&] {
         FILE* f = fopen(out_path, "wb");
         if (!f) throw Fail{std::string("jsonl: cannot open ") + out_path + " for writing"};
         try {
-            render_columns(buf, len, names, kinds, values, n_cols, n_rows, size_t(4) << 20, [&](const std::string& chunk) {
+            render_columns(buf, len, names, kinds, values, raws, n_cols, n_rows, size_t(4) << 20, [&](const std::string& chunk) {
                 if (fwrite(chunk.data(), 1, chunk.size(), f) != chunk.size())
                     throw Fail{std::string("jsonl: short write to ") + out_path};
             });
@@ -577,6 +603,55 @@ int owc_jsonl_write_columns(const char* buf, size_t len, const char* const* name
             remove(out_path);
             throw Fail{std::string("jsonl: cannot finish ") + out_path};
         }
+        return OWC_JSONL_OK;
+    });
+}
+
+int owc_jsonl_write_columns(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                            const double* values, int n_cols, size_t n_rows, const char* out_path) {
+    return write_columns_impl(buf, len, names, kinds, values, nullptr, n_cols, n_rows, out_path);
+}
+
+int owc_jsonl_write_columns_raw(const char* buf, size_t len, const char* const* names, const int32_t* kinds,
+                                const double* values, const char* const* raws, int n_cols, size_t n_rows,
+                                const char* out_path) {
+    return write_columns_impl(buf, len, names, kinds, values, raws, n_cols, n_rows, out_path);
+}
+
+int owc_jsonl_extract_raw(const char* buf, size_t len, const char* key, char* out, size_t out_cap, size_t* out_len,
+                          size_t* n_rows) {
+    return guarded([&] {
+        const size_t klen = strlen(key);
+        std::string blob;
+        blob.reserve(len / 4 + 64);
+        bool missing = false;
+        size_t rows = 0;
+        for_lines(buf, len, [&](const char* a, const char* b, size_t line) {
+            if (missing) return;
+            const char* vb = nullptr;
+            const char* ve = nullptr;
+            walk_members(a, b, line, [&](const Member& m, const char* k, size_t kl) {
+                if (kl == klen && memcmp(k, key, klen) == 0) {
+                    vb = m.val_b;
+                    ve = m.val_e;
+                }
+            });
+            if (!vb || memchr(vb, 0, (size_t)(ve - vb)) != nullptr) {
+                missing = true;
+                return;
+            }
+            blob.append(vb, (size_t)(ve - vb));
+            blob.push_back('\0');
+            ++rows;
+        });
+        if (missing) {
+            g_jsonl_err = std::string("jsonl: member '") + key + "' is missing in a row";
+            return OWC_JSONL_UNSUPPORTED;
+        }
+        if (blob.size() > out_cap) throw Fail{"jsonl: output buffer too small"};
+        memcpy(out, blob.data(), blob.size());
+        *out_len = blob.size();
+        *n_rows = rows;
         return OWC_JSONL_OK;
     });
 }

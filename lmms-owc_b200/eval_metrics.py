@@ -10,10 +10,14 @@ exactly like the reference's registry lookup. Differences, all additive:
 * the sample file is rewritten atomically (temp file + ``os.replace``) instead of in place;
 * ``--jobs N`` parses / rewrites files in N workers, ``--skip-scored`` skips files that already carry the columns;
 * launched under ``torchrun`` (``WORLD_SIZE`` > 1) the files are dealt out to the ranks by size, every rank scores its
-  own files on its own GPU (the reference spreads ``datasets.map`` over the GPUs with ``num_proc``, ``_group.py:521-535``)
-  and rank 0 prints the report;
+  own files on its own GPU and rank 0 prints the report (the reference has no multi-GPU mode for this path: its
+  ``datasets.map`` calls at ``_group.py:521-535`` pass neither ``with_rank`` nor ``num_proc``, so it runs on one device);
 * ``--io native`` reads and rewrites the files with the library's streaming JSONL scanner (``jsonl.py``) instead of
-  pandas: same records, untouched members keep their bytes, ~8x less host time per file.
+  pandas: same records, untouched members keep their bytes, ~8x less host time per file;
+* ``concept_semantic_similarity`` needs spaCy's ``en_core_web_lg`` in the reference (``_text.py:18-140``). When the
+  samples file carries pre-extracted concepts - a ``prediction_concepts`` column, or the ``last_resp_concepts`` column
+  the reference itself writes back - they are used instead (``--concepts-column``), so the
+  metric runs end to end on a machine without spaCy.
 
     python -m owc_b200.eval_metrics -i logs/schedule -m semantic_similarity
 """
@@ -57,6 +61,62 @@ def _load_items(input_file: str):
     if predictions and isinstance(predictions[0], list) and predictions[0] and isinstance(predictions[0][0], list):
         predictions = [p[0] for p in predictions]
     return df, list(zip(references, predictions, strict=True))
+
+
+# ---- pre-extracted concepts (SURVEY.md section 8(f), N4 fallback) ---------------------------------------------------
+CONCEPT_COLUMNS = ("prediction_concepts", "last_resp_concepts")
+
+
+def _scored_prediction(pred):
+    return pred[-1] if isinstance(pred, list) else pred          # _group.py:519
+
+
+def _concept_source(available, wanted: str) -> str | None:
+    """Which column of the file holds pre-extracted concepts: ``wanted`` = "auto" (the first of CONCEPT_COLUMNS that is
+    present), "none" (always run the extractor) or a column name (which must exist)."""
+    if wanted == "none":
+        return None
+    if wanted == "auto":
+        return next((c for c in CONCEPT_COLUMNS if c in available), None)
+    if wanted not in available:
+        raise KeyError(f"--concepts-column {wanted!r}: the samples file has no such column")
+    return wanted
+
+
+def _concept_extractor_from(column: str, items: list, concept_lists: list):
+    """A :class:`owc_b200.text.PreExtractedConcepts` for one file. ``last_resp_concepts`` is what the reference writes
+    back (``eval_metrics.py:93-104``): the extractor's concepts with the scored prediction appended (``_group.py:260-262``),
+    so the last element is dropped again."""
+    from .text import PreExtractedConcepts
+
+    preds = [_scored_prediction(p) for _, p in items]
+    if column == "last_resp_concepts":
+        for p, c in zip(preds, concept_lists, strict=True):
+            if not c or c[-1] != p:
+                raise ValueError(f"`last_resp_concepts` of the prediction {p!r} does not end with the prediction itself")
+        concept_lists = [list(c[:-1]) for c in concept_lists]
+    return PreExtractedConcepts(preds, concept_lists)
+
+
+class _use_extractor:
+    """Context manager: install a concept extractor in ``owc_b200.text`` for the duration of one file."""
+
+    def __init__(self, extractor) -> None:
+        self.extractor = extractor
+
+    def __enter__(self):
+        from . import text as _text
+
+        self.saved = _text.concept_extractor
+        if self.extractor is not None:
+            _text.concept_extractor = self.extractor
+        return self
+
+    def __exit__(self, *exc):
+        from . import text as _text
+
+        _text.concept_extractor = self.saved
+        return False
 
 
 def _compute(items: list, metric_names: list[str]) -> tuple[dict, dict]:
@@ -108,25 +168,43 @@ def _write_columns(input_file: str, df, columns: dict) -> None:
 # which is exactly what csrc/jsonl.cpp extracts and writes. Anything else (the concept metric's list columns, files
 # with other row shapes, empty files) takes the pandas path, so `--io native` never changes what is computed.
 _NATIVE_METRICS = {"semantic_similarity", "mean_average_semantic_similarity"}
+_NATIVE_WITH_CONCEPTS = _NATIVE_METRICS | {"concept_semantic_similarity"}   # needs a pre-extracted concepts column
 
 
 def _native_eligible(metric_names: list[str]) -> bool:
-    return all(get_metric_info(name).name in _NATIVE_METRICS for name in metric_names)
+    return all(get_metric_info(name).name in _NATIVE_WITH_CONCEPTS for name in metric_names)
 
 
-def _load_items_native(input_file: str):
-    """``(raw bytes, items)`` with the items as ``jsonl.PackedPairs`` (the ``ref[0]`` / ``pred[-1]`` strings of every
-    row in two packed columns), or ``None`` when the file needs the pandas path."""
+def _needs_concepts(metric_names: list[str]) -> bool:
+    return any(get_metric_info(name).name == "concept_semantic_similarity" for name in metric_names)
+
+
+def _load_items_native(input_file: str, metric_names: list[str] | None = None, concepts_column: str = "auto"):
+    """``(raw bytes, items, extractor)`` with the items as ``jsonl.PackedPairs`` (the ``ref[0]`` / ``pred[-1]`` strings
+    of every row in two packed columns), or ``None`` when the file needs the pandas path. With the concept metric the
+    items are ordinary tuples and ``extractor`` serves the file's pre-extracted concepts (no such column: pandas path,
+    where the spaCy extractor runs)."""
     from . import jsonl
 
     with open(input_file, "rb") as f:
         raw = f.read()
     try:
         items = jsonl.read_packed_pairs(raw)     # packed columns: no Python object per row anywhere on this path
+        extractor = None
+        if metric_names and _needs_concepts(metric_names):
+            column = None
+            if concepts_column != "none":
+                names = CONCEPT_COLUMNS if concepts_column == "auto" else (concepts_column,)
+                column = next((c for c in names if len(items) and jsonl.has_members(raw, [c])), None)
+            if column is None:
+                log.info("%s: no pre-extracted concepts column; using the pandas path", input_file)
+                return None
+            items = items.tolist()
+            extractor = _concept_extractor_from(column, items, jsonl.read_json_column(raw, column))
     except jsonl.Unsupported as exc:
         log.info("%s: %s; using the pandas path", input_file, exc)
         return None
-    return (raw, items) if len(items) else None
+    return (raw, items, extractor) if len(items) else None
 
 
 def _write_columns_native(input_file: str, raw: bytes, columns: dict) -> None:
@@ -135,17 +213,24 @@ def _write_columns_native(input_file: str, raw: bytes, columns: dict) -> None:
     jsonl.write_columns(input_file, raw, columns)
 
 
-def score_file(input_file: str, metric_names: list[str], io: str = "pandas") -> dict:
+def score_file(input_file: str, metric_names: list[str], io: str = "pandas", concepts_column: str = "auto") -> dict:
     """Score one ``*_samples_*.jsonl`` file and write the per-row columns back (``eval_metrics.py:56-133``)."""
     if io == "native" and _native_eligible(metric_names):
-        loaded = _load_items_native(input_file)
+        loaded = _load_items_native(input_file, metric_names, concepts_column)
         if loaded is not None:
-            raw, items = loaded
-            outputs, columns = _compute(items, metric_names)
+            raw, items, extractor = loaded
+            with _use_extractor(extractor):
+                outputs, columns = _compute(items, metric_names)
             _write_columns_native(input_file, raw, columns)
             return outputs
     df, items = _load_items(input_file)
-    outputs, columns = _compute(items, metric_names)
+    extractor = None
+    if _needs_concepts(metric_names):
+        column = _concept_source(df.columns, concepts_column)
+        if column is not None:
+            extractor = _concept_extractor_from(column, items, df[column].tolist())
+    with _use_extractor(extractor):
+        outputs, columns = _compute(items, metric_names)
     _write_columns(input_file, df, columns)
     return outputs
 
@@ -182,7 +267,7 @@ def _already_scored(input_file: str, metric_names: list[str]) -> bool:
     return all(m in first for m in wanted)
 
 
-def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> dict:
+def _score_files_native(todo: list[str], metric_names: list[str], jobs: int, concepts_column: str = "auto") -> dict:
     """Native I/O on worker THREADS (the scanner and the file writer run outside the GIL): a few files are parsed
     ahead of the one being scored, files are scored one after the other in this thread, and each is rewritten in
     the background while the next is being scored."""
@@ -200,14 +285,15 @@ def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> 
         nxt = 0
         for input_file in todo:
             while nxt < len(todo) and len(loads) < ahead:
-                loads.append(pool.submit(_load_items_native, todo[nxt]))
+                loads.append(pool.submit(_load_items_native, todo[nxt], metric_names, concepts_column))
                 nxt += 1
             loaded = loads.popleft().result()
             if loaded is None:
-                results[input_file] = score_file(input_file, metric_names)          # pandas path
+                results[input_file] = score_file(input_file, metric_names, concepts_column=concepts_column)   # pandas path
                 continue
-            raw, items = loaded
-            outputs, columns = _compute(items, metric_names)
+            raw, items, extractor = loaded
+            with _use_extractor(extractor):
+                outputs, columns = _compute(items, metric_names)
             results[input_file] = outputs
             if columns:
                 writes.append(pool.submit(_write_columns_native, input_file, raw, columns))
@@ -217,22 +303,41 @@ def _score_files_native(todo: list[str], metric_names: list[str], jobs: int) -> 
     return results
 
 
+def _stored_outputs(input_file: str, metric_names: list[str]) -> dict:
+    """The per-file outputs of an already scored file, recomputed from its stored per-row columns (``--skip-scored``):
+    the means the reference prints are means of exactly these columns (``eval_metrics.py:125``), so a skipped file stays
+    in the report and in the "keep the run with more samples" rule."""
+    import pandas as pd
+
+    df = pd.read_json(input_file, lines=True)
+    outputs: dict = {"_num_samples": len(df)}
+    for name in metric_names:
+        outputs[name] = float(np.mean(df[name].to_numpy(dtype=np.float64))) if len(df) else float("nan")
+    return outputs
+
+
 def score_files(input_files: list[str], metric_names: list[str], jobs: int = 1, skip_scored: bool = False,
-                io: str = "pandas") -> dict:
+                io: str = "pandas", concepts_column: str = "auto") -> dict:
     """``{file: outputs}`` for many files; with ``jobs > 1`` parsing and rewriting run in workers (threads for the
     native scanner, a process pool for pandas)."""
     if io not in ("pandas", "native"):
         raise ValueError(f"unknown io mode {io!r}: expected 'pandas' or 'native'")
     todo = [f for f in input_files if not (skip_scored and _already_scored(f, metric_names))]
+    results: dict = {}
     for f in input_files:
         if f not in todo:
-            log.info("Skipping %s: already scored", f)
-    results: dict = {}
+            log.info("Skipping %s: already scored (its stored columns feed the report)", f)
+            results[f] = _stored_outputs(f, metric_names)
     if io == "native" and _native_eligible(metric_names) and jobs > 1 and len(todo) > 1:
-        return _score_files_native(todo, metric_names, jobs)
+        results.update(_score_files_native(todo, metric_names, jobs, concepts_column))
+        return results
     if jobs <= 1 or len(todo) <= 1:
         for f in todo:
-            results[f] = score_file(f, metric_names, io=io)
+            results[f] = score_file(f, metric_names, io=io, concepts_column=concepts_column)
+        return results
+    if _needs_concepts(metric_names):       # the extractor of a file is built from its frame: keep it in one process
+        for f in todo:
+            results[f] = score_file(f, metric_names, io=io, concepts_column=concepts_column)
         return results
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
@@ -321,16 +426,35 @@ def main(args: Namespace) -> dict:
         os.environ.setdefault("OWC_TOKENIZER_THREADS", str(max(1, (os.cpu_count() or 1) // world)))   # share the host
         mine = split_files_balanced(input_files, world)[rank]
         log.info("Rank %d/%d scores %d of the files", rank, world, len(mine))
-    per_file = score_files(mine, args.metrics.split(","), jobs=getattr(args, "jobs", 1),
-                           skip_scored=getattr(args, "skip_scored", False), io=getattr(args, "io", "pandas"))
+    failure: BaseException | None = None
+    per_file: dict = {}
+    try:
+        per_file = score_files(mine, args.metrics.split(","), jobs=getattr(args, "jobs", 1),
+                               skip_scored=getattr(args, "skip_scored", False), io=getattr(args, "io", "pandas"),
+                               concepts_column=getattr(args, "concepts_column", "auto"))
+    except BaseException as exc:   # noqa: BLE001 - under torchrun the other ranks must not wait forever in the gather
+        if world == 1:
+            raise
+        failure = exc
     if world > 1:
         import torch.distributed as dist
 
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(per_file, parts, dst=0)          # a few floats per file; the data path has no collective
+        try:
+            # a few floats per file (the data path has no collective); a failed rank sends its error instead, so every
+            # rank reaches the gather and rank 0 re-raises
+            payload = (failure is None, per_file if failure is None else f"{type(failure).__name__}: {failure}")
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(payload, parts, dst=0)
+        finally:
+            dist.destroy_process_group()
+        if failure is not None:
+            raise failure
         if rank != 0:
             return {}
-        per_file = {f: out for part in parts for f, out in part.items()}
+        bad = [f"rank {r}: {msg}" for r, (ok, msg) in enumerate(parts) if not ok]
+        if bad:
+            raise RuntimeError("scoring failed on " + "; ".join(bad))
+        per_file = {f: out for _, part in parts for f, out in part.items()}
     for input_file in input_files:
         if input_file not in per_file:
             continue
@@ -360,6 +484,10 @@ def build_parser() -> ArgumentParser:
                         help="Worker processes for JSONL parsing / rewriting (scoring stays in this process; default: 1)")
     parser.add_argument("--skip-scored", action="store_true",
                         help="Skip files whose rows already carry the requested per-row metric columns")
+    parser.add_argument("--concepts-column", type=str, default="auto",
+                        help="concept_semantic_similarity: column of the samples file with pre-extracted concepts "
+                             "(`prediction_concepts`, or `last_resp_concepts` as written by the reference); 'auto' uses "
+                             "one if present, 'none' always runs the spaCy extractor (default: auto)")
     parser.add_argument("--io", choices=["pandas", "native"], default="pandas",
                         help="JSONL reader/writer: pandas (byte-identical to the reference's rewrite; default) or the "
                              "library's streaming scanner (same records, untouched members keep their bytes)")

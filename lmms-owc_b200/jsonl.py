@@ -29,11 +29,12 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["JsonlError", "Unsupported", "PackedPairs", "PackedStrings", "read_packed_pairs", "read_pairs", "read_strings", "render_columns", "write_columns", "has_members", "count_rows"]
+__all__ = ["JsonlError", "Unsupported", "PackedPairs", "PackedStrings", "read_packed_pairs", "read_pairs", "read_strings",
+           "read_raw", "read_json_column", "render_columns", "write_columns", "has_members", "count_rows"]
 
 OK, ERROR, UNSUPPORTED = 0, 1, 2
 FIRST, LAST = 0, 1
-FLOAT, INT = 0, 1
+FLOAT, INT, RAW = 0, 1, 2
 
 
 class JsonlError(ValueError):
@@ -65,6 +66,28 @@ def read_strings(raw: bytes, key: str, mode: int) -> list[str]:
         return []
     # one NUL after every row (rows containing NUL were reported as unsupported)
     return out[: out_len.value - 1].tobytes().decode("utf-8").split("\0")
+
+
+def read_raw(raw: bytes, key: str) -> list[str]:
+    """The raw JSON text of top-level member ``key`` of every row (``owc_jsonl_extract_raw``); :class:`Unsupported` when
+    a row lacks it."""
+    lib = _cabi.lib()
+    cap = len(raw) + count_rows(raw) + 1
+    out = np.empty(cap, np.uint8)
+    out_len, n_rows = C.c_size_t(), C.c_size_t()
+    rc = lib.owc_jsonl_extract_raw(raw, len(raw), key.encode(), out.ctypes.data, cap, C.byref(out_len), C.byref(n_rows))
+    if rc != OK:
+        _raise(rc)
+    if n_rows.value == 0:
+        return []
+    return out[: out_len.value - 1].tobytes().decode("utf-8").split("\0")
+
+
+def read_json_column(raw: bytes, key: str) -> list:
+    """Member ``key`` of every row, parsed (list-valued columns such as pre-extracted ``prediction_concepts``)."""
+    import json
+
+    return [json.loads(t) for t in read_raw(raw, key)]
 
 
 def count_rows(raw: bytes) -> int:
@@ -164,30 +187,76 @@ def has_members(raw: bytes, names: list[str]) -> bool:
     return bool(flag.value)
 
 
+def _is_list_column(values) -> bool:
+    return len(values) > 0 and all(isinstance(v, (list, tuple)) for v in values)
+
+
 def _column_kind(values) -> int:
+    if _is_list_column(values):
+        return RAW
     a = np.asarray(values)
     if a.dtype.kind in "iub":
         return INT
     if a.dtype.kind == "f":
         return FLOAT
-    raise Unsupported(f"column of dtype {a.dtype} (only numeric per-row columns are written natively)")
+    raise Unsupported(f"column of dtype {a.dtype} (numeric per-row columns and lists of strings / numbers are written natively)")
+
+
+def _pandas_number(v: float) -> str:
+    """A double as pandas' ``to_json`` writes it: fixed notation, 10 decimals, trailing zeros trimmed, NaN / inf -> null."""
+    v = float(v)
+    if not np.isfinite(v):
+        return "null"
+    if v == 0.0:
+        return "0.0"
+    t = "%.10f" % v
+    t = t.rstrip("0")
+    return t + "0" if t.endswith(".") else t
+
+
+def _pandas_fragment(v) -> str:
+    """One JSON value the way ``df.to_json`` renders it (ASCII-escaped strings with ``/`` escaped, numbers as above)."""
+    import json
+
+    if isinstance(v, (list, tuple)):
+        return "[" + ",".join(_pandas_fragment(x) for x in v) + "]"
+    if isinstance(v, str):
+        return json.dumps(v, ensure_ascii=True).replace("/", "\\/")
+    if isinstance(v, (bool, np.bool_)):
+        return "true" if v else "false"
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    if v is None:
+        return "null"
+    return _pandas_number(v)
 
 
 def _column_args(raw: bytes, columns: dict):
     names = list(columns)
-    kinds = (C.c_int32 * len(names))(*[_column_kind(columns[n]) for n in names])
-    vals = [np.asarray(columns[n], dtype=np.float64).reshape(-1) for n in names]
-    n_rows = vals[0].size if vals else count_rows(raw)
-    if any(v.size != n_rows for v in vals):
-        raise ValueError(f"columns of different lengths: {[v.size for v in vals]}")
+    kind_list = [_column_kind(columns[n]) for n in names]
+    kinds = (C.c_int32 * len(names))(*kind_list)
+    n_rows = len(columns[names[0]]) if names else count_rows(raw)
+    vals, blobs = [], []
+    for n, k in zip(names, kind_list):
+        if len(columns[n]) != n_rows:
+            raise ValueError(f"columns of different lengths: {[len(columns[m]) for m in names]}")
+        if k == RAW:
+            vals.append(np.zeros(n_rows))
+            blobs.append(("\0".join(_pandas_fragment(v) for v in columns[n]) + "\0").encode("utf-8"))
+        else:
+            vals.append(np.asarray(columns[n], dtype=np.float64).reshape(-1))
+            blobs.append(None)
     table = np.ascontiguousarray(np.stack(vals)) if vals else np.zeros((0, n_rows))
     arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
-    return names, arr, kinds, table, n_rows
+    raws = (C.c_char_p * len(names))(*blobs) if any(b is not None for b in blobs) else None
+    return names, arr, kinds, table, n_rows, raws
 
 
 def render_columns(raw: bytes, columns: dict) -> bytes:
     """The file's bytes with ``columns`` (name -> one number per row) replaced / appended on every line."""
-    names, arr, kinds, table, n_rows = _column_args(raw, columns)
+    names, arr, kinds, table, n_rows, raws = _column_args(raw, columns)
+    if raws is not None:
+        raise Unsupported("list-valued columns are only written to files (write_columns)")
     if n_rows != count_rows(raw):
         raise ValueError(f"{count_rows(raw)} rows in the file, {n_rows} values per column")
     cap = len(raw) + n_rows * (sum(len(n.encode()) + 4 for n in names) + 40 * len(names) + 4) + 64
@@ -205,10 +274,14 @@ def write_columns(path: str, raw: bytes, columns: dict) -> None:
     replaces the samples file (a crash cannot truncate it)."""
     if not columns:
         return
-    names, arr, kinds, table, n_rows = _column_args(raw, columns)
+    names, arr, kinds, table, n_rows, raws = _column_args(raw, columns)
     tmp = path + ".tmp"
-    rc = _cabi.lib().owc_jsonl_write_columns(raw, len(raw), arr, kinds, table.ctypes.data_as(C.c_void_p), len(names),
-                                             n_rows, os.fsencode(tmp))
+    if raws is None:
+        rc = _cabi.lib().owc_jsonl_write_columns(raw, len(raw), arr, kinds, table.ctypes.data_as(C.c_void_p), len(names),
+                                                 n_rows, os.fsencode(tmp))
+    else:
+        rc = _cabi.lib().owc_jsonl_write_columns_raw(raw, len(raw), arr, kinds, table.ctypes.data_as(C.c_void_p), raws,
+                                                     len(names), n_rows, os.fsencode(tmp))
     if rc != OK:
         _raise(rc)
     os.replace(tmp, path)

@@ -16,7 +16,7 @@ from .engine import Engine
 from .tokenizer import HostTokenizer
 
 __all__ = ["encode_sentence_bert", "concept_extraction_spacy", "configure", "reset", "get_engine",
-           "encode_unique", "MODEL_NAME"]
+           "encode_unique", "PreExtractedConcepts", "MODEL_NAME"]
 
 MODEL_NAME = "sentence-transformers/all-MiniLM-L6-v2"  # _text.py:161
 
@@ -106,6 +106,42 @@ def encode_sentence_bert(batch: dict, rank: int | None = None, **kwargs) -> dict
         raise NotImplementedError
 
     return batch
+
+
+class PreExtractedConcepts:
+    """Concept extractor backed by concepts that were extracted elsewhere (SURVEY.md section 8(f), N4 fallback).
+
+    spaCy + ``en_core_web_lg`` cannot be installed offline, so ``concept_semantic_similarity`` can take the concepts of
+    every prediction from the samples file instead: a ``prediction_concepts`` column (what the reference's
+    ``concept_extraction_spacy(..., skip_words=..., remove_prefix_words=True)`` returns for the scored prediction,
+    ``_group.py:247-257``), or the ``last_resp_concepts`` column the reference itself writes back
+    (``eval_metrics.py:93-104``: the same list with the prediction appended). Install an instance in
+    ``owc_b200.text.concept_extractor``; it has the extractor's call signature and fails loudly for a prediction it has
+    no concepts for.
+    """
+
+    def __init__(self, predictions, concepts) -> None:
+        if len(predictions) != len(concepts):
+            raise ValueError("one concept list per prediction")
+        self.table: dict[str, list[str]] = {}
+        for p, c in zip(predictions, concepts):
+            c = [str(x) for x in c]
+            if p in self.table and self.table[p] != c:
+                raise ValueError(f"two different concept lists for the prediction {p!r}")
+            self.table[p] = c
+
+    def __call__(self, batch: dict, **kwargs) -> dict:
+        input_column = kwargs.pop("input_column", "text")
+        output_column = kwargs.pop("output_column", f"{input_column}_concepts")
+        if input_column not in batch:
+            raise ValueError(f"{input_column} missing in dataset")
+        texts = batch[input_column]
+        try:
+            batch[output_column] = ([list(self.table[t]) for t in texts] if isinstance(texts, list)
+                                    else list(self.table[texts]))
+        except KeyError as exc:
+            raise KeyError(f"no pre-extracted concepts for the prediction {exc.args[0]!r}") from None
+        return batch
 
 
 def concept_extraction_spacy(batch: dict, **kwargs) -> dict:

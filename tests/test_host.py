@@ -345,4 +345,11 @@ def test_eval_metrics_parallel_io_is_byte_identical(oracle_backed, tmp_path):
         assert f.read_bytes() == g.read_bytes()
     before = {f: f.stat().st_mtime_ns for f in root.rglob("*.jsonl")}
     again = EM.main(EM.build_parser().parse_args(["-i", str(root), "-m", metrics, "--skip-scored"]))
-    assert again == {} and before == {f: f.stat().st_mtime_ns for f in root.rglob("*.jsonl")}
+    assert before == {f: f.stat().st_mtime_ns for f in root.rglob("*.jsonl")}            # scored files are left alone ...
+    # ... but stay in the report: their outputs are recomputed from the stored columns (10 decimals on disk)
+    assert again.keys() == serial.keys()
+    for task in serial:
+        assert again[task].keys() == serial[task].keys()
+        for model, out in serial[task].items():
+            assert again[task][model].keys() == out.keys() and again[task][model]["_num_samples"] == out["_num_samples"]
+            assert all(abs(again[task][model][k] - v) < 1e-9 for k, v in out.items())

@@ -305,10 +305,129 @@ def test_cli_native_io_scores_like_the_pandas_path(minilm, monkeypatch, tmp_path
             pd.testing.assert_frame_equal(got[want.columns], want, check_exact=False, atol=1e-9, rtol=0)
             if "odd" not in str(f):                                 # native rewrite: source bytes kept
                 assert b'"note": "a/b \xc3\xa9"' in g.read_bytes()
-    # the concept metric writes list columns: not eligible, pandas path, same behaviour as without the flag
-    assert not EM._native_eligible(["concept_semantic_similarity"])
+    # the concept metric is eligible too: with a pre-extracted concepts column it stays native (list columns are written
+    # as raw fragments), without one the file takes the pandas path (test_cli_concepts_from_the_samples_file)
+    assert EM._native_eligible(["concept_semantic_similarity"])
     with pytest.raises(ValueError):
         EM.score_files([], ["semantic_similarity"], io="arrow")
+
+
+def test_cli_concepts_from_the_samples_file(minilm, monkeypatch, tmp_path):
+    """N4 fallback: `concept_semantic_similarity` end to end WITHOUT a concept extractor, from a
+    `prediction_concepts` column of the samples file, and re-scoring from the `last_resp_concepts` column the metric
+    writes back - pandas and native I/O write the same records, equal to the run with the extractor installed (which is
+    pinned to the reference's own output in tests/test_host.py)."""
+    import shutil
+
+    import pandas as pd
+
+    from oracle import metrics_ref
+    from owc_b200 import eval_metrics as EM
+    from owc_b200 import text as T
+    from owc_b200.tokenizer import HostTokenizer
+    from test_host import OracleEngine
+
+    monkeypatch.setattr(T, "sentence_bert_model", OracleEngine(minilm))
+    monkeypatch.setattr(T, "sentence_bert_processor", HostTokenizer(minilm.vocab, "bert"))
+    b = minilm
+    cls = [str(s) for s in b.gold["class_names"]]
+    cpreds = [str(s) for s in b.gold["concept_preds"]]
+    tg = b.gold["targets"]
+    skip = [w for cat in __import__("owc_b200.metrics._group", fromlist=["x"])._SKIP_WORDS_GROUPS.values() for w in cat]
+    extracted = metrics_ref.simple_concepts({"prediction": cpreds}, input_column="prediction", output_column="c",
+                                            skip_words=skip, remove_prefix_words=True)["c"]
+
+    def write(root, with_column):
+        run = root / "caltech101" / "model-0"
+        run.mkdir(parents=True)
+        with open(run / "r_samples_caltech101.jsonl", "w", encoding="utf-8") as f:
+            for i, p in enumerate(cpreds):
+                row = {"doc_id": i, "target": cls[tg[i]], "filtered_resps": [p], "note": "a/b é"}
+                if with_column:
+                    row["prediction_concepts"] = extracted[i]
+                f.write(json.dumps(row, ensure_ascii=False) + "\n")
+        return run / "r_samples_caltech101.jsonl"
+
+    args = lambda root, *extra: EM.build_parser().parse_args(["-i", str(root), "-m", "concept_semantic_similarity", *extra])  # noqa: E731
+    # 1. the extractor installed, no column (what the existing tests pin to the reference)
+    f_ext = write(tmp_path / "ext" / "logs", False)
+    monkeypatch.setattr(T, "concept_extractor", metrics_ref.simple_concepts)
+    want_out = EM.main(args(tmp_path / "ext" / "logs"))
+    want = pd.read_json(f_ext, lines=True)
+    monkeypatch.setattr(T, "concept_extractor", None)
+    # 2. no extractor at all: the column feeds the metric, through pandas and through the native scanner
+    f_pd = write(tmp_path / "pd" / "logs", True)
+    f_nat = write(tmp_path / "nat" / "logs", True)
+    assert EM.main(args(tmp_path / "pd" / "logs")) == want_out
+    assert EM.main(args(tmp_path / "nat" / "logs", "--io", "native")) == want_out
+    assert T.concept_extractor is None                              # restored after every file
+    cols = ["concept_semantic_similarity", "last_resp_concepts", "last_resp_concepts_similarities"]
+    for f in (f_pd, f_nat):
+        got = pd.read_json(f, lines=True)
+        assert got["last_resp_concepts"].tolist() == want["last_resp_concepts"].tolist()
+        assert np.abs(got["concept_semantic_similarity"] - want["concept_semantic_similarity"]).max() < 1e-9
+        for x, y in zip(got["last_resp_concepts_similarities"], want["last_resp_concepts_similarities"], strict=True):
+            assert np.abs(np.asarray(x) - np.asarray(y)).max() < 1e-9
+        assert got["prediction_concepts"].tolist() == extracted
+    assert b'"note": "a/b \xc3\xa9"' in f_nat.read_bytes()          # native rewrite keeps untouched members' bytes
+    # byte-level: the native writer formats the list columns exactly as pandas does
+    line_pd = f_pd.read_bytes().splitlines()[0].decode()
+    line_nat = f_nat.read_bytes().splitlines()[0].decode()
+    for c in cols:
+        frag = line_pd[line_pd.index(f'"{c}":'):]
+        frag = frag[:frag.index(',"', 1) if ',"' in frag[1:] else len(frag) - 1] if c != cols[-1] else frag.rstrip("}")
+        assert frag in line_nat, c
+    # 3. re-scoring a file the metric (or the reference) has already written: `last_resp_concepts` is the source
+    f_re = tmp_path / "re" / "logs" / "caltech101" / "model-0"
+    f_re.mkdir(parents=True)
+    df = want.drop(columns=["concept_semantic_similarity", "last_resp_concepts_similarities"])
+    df.to_json(f_re / "r_samples_caltech101.jsonl", lines=True, orient="records")
+    shutil.copytree(tmp_path / "re", tmp_path / "re_nat")
+    assert EM.main(args(tmp_path / "re" / "logs")) == want_out
+    assert EM.main(args(tmp_path / "re_nat" / "logs", "--io", "native")) == want_out
+    again = pd.read_json(f_re / "r_samples_caltech101.jsonl", lines=True)
+    assert again["last_resp_concepts"].tolist() == want["last_resp_concepts"].tolist()
+    # 4. nothing to extract with and nothing extracted: the reference's requirement (spaCy) surfaces, nothing is made up
+    write(tmp_path / "none" / "logs", False)
+    with pytest.raises(ImportError):
+        EM.main(args(tmp_path / "none" / "logs"))
+    with pytest.raises(KeyError):
+        EM.main(args(tmp_path / "none" / "logs", "--concepts-column", "my_concepts"))
+    bad = T.PreExtractedConcepts(["a"], [["x"]])
+    with pytest.raises(KeyError, match="no pre-extracted concepts"):
+        bad({"prediction": ["b"]}, input_column="prediction")
+    with pytest.raises(ValueError):
+        T.PreExtractedConcepts(["a", "a"], [["x"], ["y"]])
+
+
+def test_scanner_is_strict_about_control_bytes_and_trailing_data():
+    """A raw control byte inside a string the metric uses, or bytes after the closing brace, are not JSON: pandas raises
+    on both, so the native path must not score such a file (a raw NUL used to split a row in two)."""
+    import pandas as pd
+    from io import BytesIO
+
+    from owc_b200 import jsonl
+
+    good = b'{"target": "a", "filtered_resps": ["b"]}\n'
+    assert jsonl.read_pairs(good) == [("a", "b")]
+    for ctl in (b"\x00", b"\x01", b"\x1f", b"\n"[:0] + b"\t"):
+        raw = b'{"target": "a' + ctl + b'b", "filtered_resps": ["c"]}\n' + good
+        with pytest.raises(jsonl.Unsupported):
+            jsonl.read_pairs(raw)                      # -> the CLI falls back to pandas ...
+        with pytest.raises(jsonl.Unsupported):
+            jsonl.read_packed_pairs(raw)
+        try:                                           # ... whose verdict (an error for NUL, leniency for some others)
+            pd.read_json(BytesIO(raw), lines=True)     # is then exactly the reference's verdict
+        except ValueError:
+            pass
+    for junk in (b'{"target": "a", "filtered_resps": ["b"]} junk\n', b'{"target": "a", "filtered_resps": ["b"]}{}\n', b"{} x\n"):
+        with pytest.raises(jsonl.JsonlError, match="trailing data"):
+            jsonl.read_pairs(junk + good)
+        with pytest.raises(jsonl.JsonlError, match="trailing data"):
+            jsonl.render_columns(junk, {"s": [1.0]})
+        with pytest.raises(ValueError):
+            pd.read_json(BytesIO(junk), lines=True)
+    assert jsonl.read_pairs(b'  {"target": "a", "filtered_resps": ["b"]}  \r\n') == [("a", "b")]   # surrounding whitespace is fine
 
 
 def test_packed_route_equals_the_string_route():

@@ -266,3 +266,49 @@ def test_cli_deals_files_to_ranks_world2(tmp_path, monkeypatch):
     assert results[0]["default_rank"] == 0 and results[1]["default_rank"] == 1  # each rank on its own GPU
     for f in EM.find_input_files(one):
         assert open(f, "rb").read() == open(f.replace(one, two), "rb").read()  # every file scored exactly once
+
+
+def _cli_failing_worker(rank, world, port, root, queue):
+    sys.path.insert(0, ROOT)
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank)})
+    torch.set_num_threads(1)
+    from owc_b200 import eval_metrics as EM
+    from owc_b200 import text as T
+
+    arch, sd, tok, *_ = _small_setup()
+    T.sentence_bert_model, T.sentence_bert_processor = _PairEngine(arch, sd), tok
+    try:
+        EM.main(EM.build_parser().parse_args(["-i", root, "-m", "semantic_similarity", "--io", "native", "--log-level", "ERROR"]))
+        queue.put({"rank": rank, "error": None})
+    except BaseException as exc:   # noqa: BLE001
+        queue.put({"rank": rank, "error": f"{type(exc).__name__}: {exc}", "group_alive": dist.is_initialized()})
+    finally:
+        T.sentence_bert_model = T.sentence_bert_processor = None
+
+
+def test_cli_rank_failure_reaches_rank0_instead_of_hanging(tmp_path):
+    """One rank's file is broken: that rank raises, and rank 0 (which is waiting in the gather of the per-file outputs)
+    gets the error and raises too, instead of blocking forever; the process group is torn down on both."""
+    from owc_b200 import eval_metrics as EM
+
+    arch, sd, tok, classes, preds, targets = _small_setup()
+    root = str(tmp_path / "logs")
+    _write_cli_logs(root, classes, preds, targets)
+    files = EM.find_input_files(root)
+    deal = EM.split_files_balanced(files, 2)
+    with open(deal[1][0], "a", encoding="utf-8") as f:          # a file that rank 1 owns
+        f.write('{"doc_id": 1, "target": "x", "filtered_resps": ["y"]} trailing junk\n')
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cli_failing_worker, args=(r, 2, port, root, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {r["rank"]: r for r in (queue.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "trailing data" in results[1]["error"] or "Expected object or value" in results[1]["error"] or "ValueError" in results[1]["error"]
+    assert results[0]["error"] is not None and "rank 1" in results[0]["error"]
+    assert not results[0]["group_alive"] and not results[1]["group_alive"]
