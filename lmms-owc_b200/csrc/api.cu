@@ -84,6 +84,7 @@ struct owc_ctx {
   int wide_deep = 1;       // FFN2 on the 5-stage / single-residual-buffer variant of the residual epilogue (env OWC_WIDE_DEEP)
   int wide_rot = 0;        // clusters start their column-tile sweeps at different tiles (env OWC_WIDE_ROT=1; measured: QKV +5 %,
                            // the whole encode -1.5 % - the step is power-capped, not bound by any one kernel)
+  int wide_ffn2_split = 1; // FFN2: the three column tiles of a row-block pair on three neighbouring clusters (env OWC_WIDE_FFN2_SPLIT)
   int wide_waves = 8;      // row-block pairs per cluster and chunk on that path (env OWC_WIDE_WAVES)
   std::map<const void*, size_t> smem_attr;   // kernels whose dynamic shared-memory opt-in was set on THIS device
   long long* wide_dbg = nullptr;             // [32] cycle counters of the instrumented wide GEMM (env OWC_WIDE_DBG=1), else nullptr
@@ -366,16 +367,25 @@ static int wide_splits(const owc_ctx* c, int M, int tiles) {
   return (tiles + tpi - 1) / tpi;
 }
 
+// FFN2 (K = 3072, three column tiles): with one row-block pair per cluster the 74 clusters hold 74 x 1.5 MB of A blocks in
+// flight - more than the L2 keeps next to everything else - and every column tile re-reads its A block from DRAM. Splitting
+// the three tiles of a pair over three NEIGHBOURING clusters (item = pair x tile) puts a third as many A blocks in flight,
+// read from DRAM once and from L2 twice.
+static int ffn2_splits(const owc_ctx* c, int M, int tiles) {
+  const int s = wide_splits(c, M, tiles);
+  return c->wide_ffn2_split ? tiles : s;
+}
+
 template <int EPI>
 static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
-                            WideArgs g, int shape_cat) {
+                            WideArgs g, int shape_cat, int force_splits = 0) {
   OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI, false>, WideCfg<EPI>::SMEM_BYTES));
   if (c->wide_dbg) OWC_TRY(ensure_smem_attr(c, k_gemm_wide<EPI, true>, WideCfg<EPI>::SMEM_BYTES));
   if (g.K % 64 != 0 || g.K <= 0 || g.N % 256 != 0 || g.N <= 0 || g.M <= 0) return fail("wide GEMM: bad shape %d x %d x %d", g.M, g.N, g.K);
   const int clusters_max = std::max(1, c->sm_count / 2);
   const int tiles = g.N / 256;
   g.n_pairs = (g.M + 255) / 256;
-  g.splits = wide_splits(c, g.M, tiles);
+  g.splits = force_splits > 0 ? std::min(force_splits, tiles) : wide_splits(c, g.M, tiles);
   g.tiles_per_item = (tiles + g.splits - 1) / g.splits;
   const int clusters = std::min(g.n_pairs * g.splits, clusters_max);
   g.dbg = c->wide_dbg;
@@ -463,6 +473,7 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* ag = getenv("OWC_ATTN_GRP")) c->attn_grp = atoi(ag) != 0;
   if (const char* wd2 = getenv("OWC_WIDE_DEEP")) c->wide_deep = atoi(wd2) != 0;
   if (const char* wr = getenv("OWC_WIDE_ROT")) c->wide_rot = atoi(wr) != 0;
+  if (const char* fs = getenv("OWC_WIDE_FFN2_SPLIT")) c->wide_ffn2_split = atoi(fs) != 0;
   const bool want_wide_dbg = getenv("OWC_WIDE_DBG") && atoi(getenv("OWC_WIDE_DBG")) != 0;
   c->chunk_default = chunk_tokens <= 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
@@ -762,6 +773,11 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
 // ------------------------------------------------------------------------------------------------
 // encoder forward over one chunk of whole sequences
 // ------------------------------------------------------------------------------------------------
+// k_embed_ln: persistent warps (LayerNorm parameters in registers for the warp's lifetime), a few CTAs per SM
+static unsigned embed_grid(const owc_ctx* c, int n_seq) {
+  return static_cast<unsigned>(std::max(1, std::min((n_seq + 3) / 4, c->sm_count * 8)));
+}
+
 template <typename T>
 static int launch_attn(owc_encoder* e, const AttnArgs& aa) {
   owc_ctx* c = e->ctx;
@@ -893,7 +909,7 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
   ea.x = e->x; ea.xb = bf ? e->xb : nullptr; ea.status = c->d_status;
   {
     ProfScope prof(c, OWC_KCAT_EMBED);
-    DISPATCH_NV(H, k_embed_ln<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(ea));
+    DISPATCH_NV(H, k_embed_ln<NV, false><<<embed_grid(c, n_seq), 128, 0, c->stream>>>(ea));
   }
   OWC_TRY(check_launch(c, "k_embed_ln"));
 
@@ -992,7 +1008,7 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
   ea.x = e->x; ea.xb = e->xb; ea.status = c->d_status; ea.stats = e->st2;
   {
     ProfScope prof(c, OWC_KCAT_EMBED);
-    DISPATCH_NV(H, k_embed_ln<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(ea));
+    DISPATCH_NV(H, k_embed_ln<NV, true><<<embed_grid(c, n_seq), 128, 0, c->stream>>>(ea));
   }
   OWC_TRY(check_launch(c, "k_embed_ln"));
 
@@ -1023,7 +1039,9 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
     aa.n_grp = static_cast<int>(grp.size()) - 1;
   }
 
-  const int res_slots = 2 * wide_splits(c, M, H / 256);   // slots the O-projection / FFN2 kernels of this chunk write
+  const int o_slots = 2 * wide_splits(c, M, H / 256);     // partial-statistics slots the O-projection of this chunk writes (st1)
+  const int f2_splits = ffn2_splits(c, M, H / 256);
+  const int res_slots = 2 * f2_splits;                     // ... and FFN2 (st2)
   const long long stride = e->cap;
   for (int l = 0; l < a.layers; ++l) {
     const LayerW& L = e->layers[l];
@@ -1043,13 +1061,13 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
     OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_O));
     g = WideArgs{};
     g.M = M; g.N = I; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
-    g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.slots_in = res_slots;
+    g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.slots_in = o_slots;
     OWC_TRY(launch_gemm_wide<WEPI_FOLD_GELU_BF16>(c, e->tm_xb, L.tmf_w1, e->tmo_f, e->tmo_f, g, OWC_KCAT_GEMM_FFN1));
     g = WideArgs{};
     g.M = M; g.N = H; g.K = I; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
-    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.slots_in = res_slots; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
-    if (c->wide_deep) OWC_TRY(launch_gemm_wide<WEPI_RES_STATS_DEEP>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2));
-    else OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2));
+    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.slots_in = o_slots; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
+    if (c->wide_deep) OWC_TRY(launch_gemm_wide<WEPI_RES_STATS_DEEP>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
+    else OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
   }
   const LayerW& LL = e->layers[a.layers - 1];
   {
@@ -1103,6 +1121,7 @@ static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t*
   fa.ln_eps = a.ln_eps;
   fa.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(H / a.heads));
   fa.dbg = c->fused_dbg ? e->fdbg : nullptr;
+  fa.no_groups = c->attn_grp ? 0 : 1;
   // role ablation (wrong results by construction) exists for tools/fused_ablate.py only: it needs OWC_DEBUG_HOOKS=1 as well,
   // so a stray OWC_FUSED_ABLATE in a production environment cannot corrupt embeddings silently
   if (const char* ab = getenv("OWC_FUSED_ABLATE")) {
@@ -1127,7 +1146,7 @@ static int encode_all_fused(owc_encoder* e, const int32_t* d_ids, const int32_t*
       ea.x = e->fx; ea.xb = nullptr; ea.status = c->d_status;
       {
         ProfScope prof(c, OWC_KCAT_EMBED);
-        k_embed_ln<3><<<(nseq + 3) / 4, 128, 0, c->stream>>>(ea);
+        k_embed_ln<3, false><<<embed_grid(c, nseq), 128, 0, c->stream>>>(ea);
       }
       OWC_TRY(check_launch(c, "k_embed_ln"));
       fa.blk_seq = static_cast<const int32_t*>(d_blk) + b0;

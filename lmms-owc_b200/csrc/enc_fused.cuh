@@ -50,6 +50,7 @@ struct FusedArgs {
   const float *bqkv, *bo, *ln1g, *ln1b, *b1, *b2, *ln2g, *ln2b;   // layer 0
   float ln_eps;
   float scale_log2;          // head_dim^-0.5 * log2(e)
+  int no_groups;             // A/B: 1 = one sequence per attention tile (OWC_ATTN_GRP=0)
   int ablate;                // debug: bit0 skip attention math, bit1 skip GELU, bit2 skip LayerNorm math, bit3 skip T1 drains (wrong results)
   long long* dbg;            // optional timeline stamps of cluster 0 / leader (clock64), nullptr in production
 };
@@ -72,7 +73,8 @@ constexpr int OFF_QKV = OFF_U + 16384;      // 2 x (128 x 192) = 2 x 24576: one 
 constexpr int OFF_FC = OFF_U;               // 2 x 32768
 constexpr int OFF_RING = OFF_U + 65536;     // 163840
 constexpr int OFF_TAIL = OFF_RING + SLOTS * SLOT;   // 221184
-constexpr int TAIL_BYTES = 1024 + 4096 + 3 * 384 * 4 + 3 * 384 * 4;   // barriers / tables, LayerNorm statistics, LayerNorm bias|gamma|beta, QKV bias
+constexpr int OFF_GRP = 1024 + 4096 + 3 * 384 * 4 + 3 * 384 * 4;      // attention groups of the block: uint8 [<= 130] + count
+constexpr int TAIL_BYTES = OFF_GRP + 256;   // barriers / tables, LayerNorm statistics, LayerNorm bias|gamma|beta, QKV bias, groups
 constexpr int SMEM_BYTES = OFF_TAIL + TAIL_BYTES + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t TM_X = 0, TM_T1 = 384;   // TMEM column offsets
@@ -249,6 +251,120 @@ __device__ __forceinline__ void attn_head_smem(const uint8_t* qkv, uint8_t* ao_t
   }
 }
 
+// Several short sequences of the block in ONE 16 x 16 tile (see attn_group16 in attn_mma.cuh): a group is a run of
+// consecutive sequences with at most 16 tokens together, rows [beg, beg + T) of the block; seq_row[s_first .. s_last] are
+// the sequences' first rows. Block-diagonal mask: tile row i only sees the keys [lo_i, hi_i) of its own sequence. The
+// instruction count is that of ONE sequence in attn_head_smem<16>, so label-length inputs (2-3 sequences per tile) spend
+// less than half the SIMT time per head.
+template <typename PreStore>
+__device__ __forceinline__ void attn_group_smem(const uint8_t* qkv, uint8_t* ao_tile, int beg, int T, const int* seq_row,
+                                                int s_first, int s_last, int lane, int cb, float scale_log2,
+                                                PreStore pre_store) {
+  constexpr int NT = 2, DN = 4;
+  const int g = lane >> 2, t4 = lane & 3;
+  auto row_of = [&](int i) { return min(beg + i, 127); };
+  int lo = 0, hi = 0;
+  for (int sq = s_first; sq < s_last; ++sq) {
+    const int b = seq_row[sq] - beg, e = seq_row[sq + 1] - beg;
+    if (lane >= b && lane < e) { lo = b; hi = e; }
+  }
+  const int r0 = g, r1 = g + 8;
+  const int lo0 = __shfl_sync(0xffffffffu, lo, r0), hi0 = __shfl_sync(0xffffffffu, hi, r0);
+  const int lo1 = __shfl_sync(0xffffffffu, lo, r1), hi1 = __shfl_sync(0xffffffffu, hi, r1);
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { s[nt][0] = 0.f; s[nt][1] = 0.f; s[nt][2] = 0.f; s[nt][3] = 0.f; }
+  const int qr0 = row_of(r0), qr1 = row_of(r1);
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t af[4];
+    af[0] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr0, 2 * ks) + t4 * 4);
+    af[1] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr1, 2 * ks) + t4 * 4);
+    af[2] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr0, 2 * ks + 1) + t4 * 4);
+    af[3] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, qr1, 2 * ks + 1) + t4 * 4);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 < T) {   // warp-uniform
+        const int kr = row_of(nt * 8 + g);
+        uint32_t bf[2];
+        bf[0] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, kr, 4 + 2 * ks) + t4 * 4);
+        bf[1] = *reinterpret_cast<const uint32_t*>(qkv_chunk(qkv, kr, 5 + 2 * ks) + t4 * 4);
+        mma_bf16_16816(s[nt], af, bf);
+      }
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = nt * 8 + t4 * 2 + (e & 1);
+      const bool ok = (e < 2) ? (j >= lo0 && j < hi0) : (j >= lo1 && j < hi1);
+      const float v = ok ? s[nt][e] * scale_log2 : -INFINITY;
+      s[nt][e] = v;
+      if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  m0 = (hi0 > lo0) ? m0 : 0.f;   // tile rows past the group have no key: keep (-inf) - (-inf) out of the exponent
+  m1 = (hi1 > lo1) ? m1 : 0.f;
+  uint32_t pk[NT][2];
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    float e0, e1, e2, e3;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s[nt][0] - m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s[nt][1] - m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(s[nt][2] - m1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(s[nt][3] - m1));
+    const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+    const __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+    sum0 += __low2float(p01) + __high2float(p01);
+    sum1 += __low2float(p23) + __high2float(p23);
+    pk[nt][0] = *reinterpret_cast<const uint32_t*>(&p01);
+    pk[nt][1] = *reinterpret_cast<const uint32_t*>(&p23);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  float o[DN][4];
+#pragma unroll
+  for (int dn = 0; dn < DN; ++dn) { o[dn][0] = 0.f; o[dn][1] = 0.f; o[dn][2] = 0.f; o[dn][3] = 0.f; }
+  {
+    const uint32_t af[4] = {pk[0][0], pk[0][1], pk[1][0], pk[1][1]};
+    const int vr = row_of(lane & 15);
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      uint32_t bf[2];
+      ldmatrix_x2_trans(bf, qkv_chunk(qkv, vr, 8 + dn));
+      mma_bf16_16816(o[dn], af, bf);
+    }
+  }
+  float inv0, inv1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(fmaxf(sum0, 1.0f)));   // real rows sum to >= 1; rows past the group are not stored
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(fmaxf(sum1, 1.0f)));
+  pre_store();
+  const int gr0 = beg + r0, gr1 = beg + r1;
+  if (r0 < T) {
+    uint8_t* p0 = ao_tile + gr0 * 128 + t4 * 4;
+    const int sw0 = gr0 & 7;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn)
+      *reinterpret_cast<uint32_t*>(p0 + (((cb + dn) ^ sw0) << 4)) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+  }
+  if (r1 < T) {
+    uint8_t* p1 = ao_tile + gr1 * 128 + t4 * 4;
+    const int sw1 = gr1 & 7;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn)
+      *reinterpret_cast<uint32_t*>(p1 + (((cb + dn) ^ sw1) << 4)) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+  }
+}
+
 // Debug-only phase accounting: time since the previous mark is charged to bucket i.
 template <bool ON>
 struct PhaseAcc {
@@ -301,6 +417,8 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   float* stat_s = reinterpret_cast<float*>(tail + 1024);   // [NSIMT][32][2]
   float* lnp = reinterpret_cast<float*>(tail + 1024 + 4096);   // [3][384]: bias | gamma | beta of the next LayerNorm
   float* bqkv_s = lnp + 3 * 384;                               // [3][384]: q | k | v projection bias of the current layer
+  uint8_t* grp_first = tail + OFF_GRP;                         // [n_grp + 1] first sequence (block-relative) of each attention group
+  int* n_grp_s = reinterpret_cast<int*>(tail + OFF_GRP + 192);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -676,6 +794,22 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       named_bar_sync(1, NSIMT * 32);   // everyone is done with the previous block's sequence table
       for (int i = threadIdx.x; i <= nseq; i += NSIMT * 32) seq_row[i] = __ldg(a.cu + s0 + i) - a.tok0 - row0;
       named_bar_sync(1, NSIMT * 32);
+      if (threadIdx.x == 0) {
+        // attention groups: runs of consecutive sequences with at most 16 tokens together share one 16 x 16 tile; a
+        // longer sequence is alone in its group. Read after the barriers that open the first attention block.
+        int ng = 0, rows = 0;
+        grp_first[0] = 0;
+        for (int i = 0; i < nseq; ++i) {
+          const int len = seq_row[i + 1] - seq_row[i];
+          if (rows > 0 && rows + len > 16) {
+            grp_first[++ng] = static_cast<uint8_t>(i);
+            rows = 0;
+          }
+          rows += len;
+        }
+        if (nseq > 0) grp_first[++ng] = static_cast<uint8_t>(nseq);
+        *n_grp_s = a.no_groups ? -1 : ng;
+      }
       FZ_STAMP();
       // ---- load the block's residual rows: global fp32 -> TMEM x + XB ----
       {
@@ -757,13 +891,26 @@ k_encoder_fused(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             auto pre_store = [&]() {   // the O-projection of the previous head pair has read the AO tile
               if (!ao_ok) { mbar_wait(ao_free, (n_pair & 1) ^ 1); ao_ok = true; }
             };
-            for (int i = gw; i < ((ablate & 1) ? 0 : nseq); i += NSIMT / 2) {
-              const int beg = seq_row[i];
-              const int T = seq_row[i + 1] - beg;
-              if (T <= 0) continue;
-              if (T <= 16) attn_head_smem<16>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
-              else if (T <= 32) attn_head_smem<32>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
-              else attn_head_smem<64>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+            const int n_grp = *n_grp_s;
+            if (n_grp >= 0) {
+              for (int u = gw; u < ((ablate & 1) ? 0 : n_grp); u += NSIMT / 2) {
+                const int s_first = grp_first[u], s_last = grp_first[u + 1];
+                const int beg = seq_row[s_first];
+                const int T = seq_row[s_last] - beg;
+                if (T <= 0) continue;
+                if (T <= 16) attn_group_smem(qkv_g, AO, beg, T, seq_row, s_first, s_last, lane, cb, a.scale_log2, pre_store);
+                else if (T <= 32) attn_head_smem<32>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+                else attn_head_smem<64>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+              }
+            } else {   // OWC_ATTN_GRP=0: one sequence per tile (A/B)
+              for (int i = gw; i < ((ablate & 1) ? 0 : nseq); i += NSIMT / 2) {
+                const int beg = seq_row[i];
+                const int T = seq_row[i + 1] - beg;
+                if (T <= 0) continue;
+                if (T <= 16) attn_head_smem<16>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+                else if (T <= 32) attn_head_smem<32>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+                else attn_head_smem<64>(qkv_g, AO, beg, T, lane, cb, a.scale_log2, pre_store);
+              }
             }
             pa.mark(4);
             pa.event(3);   // own attention done
