@@ -541,6 +541,8 @@ def measure_sweep(d: Dist, steps: int, warmup: int) -> dict:
 
     sw = make_sweep()
     arch, tasks = sw["arch"], sw["tasks"]
+    if d.world > 1:   # the ranks share the host's cores: each tokenizer takes its share instead of all of them (as the CLI does)
+        os.environ.setdefault("OWC_TOKENIZER_THREADS", str(max(1, (os.cpu_count() or 1) // d.world)))
     tok = HostTokenizer(sw["vocab"], "bert")
     eng = Engine(arch, random_state_dict(arch), device=d.local_rank)
     flat = [(ds, key, len(f["predictions"])) for ds, t in tasks.items() for key, f in t["files"].items()]
