@@ -20,6 +20,7 @@
 #include "enc_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_wide.cuh"
+#include "qkv_attn.cuh"
 #include "kernels.cuh"
 
 using namespace owc;
@@ -85,6 +86,7 @@ struct owc_ctx {
   int wide_rot = 0;        // clusters start their column-tile sweeps at different tiles (env OWC_WIDE_ROT=1; measured: QKV +5 %,
                            // the whole encode -1.5 % - the step is power-capped, not bound by any one kernel)
   int wide_ffn2_split = 1; // FFN2: the three column tiles of a row-block pair on three neighbouring clusters (env OWC_WIDE_FFN2_SPLIT)
+  int qkv_attn = 0;        // wide path: attention in the QKV projection's epilogue for sequences <= 64 tokens (env OWC_QKV_ATTN)
   int wide_waves = 8;      // row-block pairs per cluster and chunk on that path (env OWC_WIDE_WAVES)
   std::map<const void*, size_t> smem_attr;   // kernels whose dynamic shared-memory opt-in was set on THIS device
   long long* wide_dbg = nullptr;             // [32] cycle counters of the instrumented wide GEMM (env OWC_WIDE_DBG=1), else nullptr
@@ -111,6 +113,10 @@ struct LayerW {
   const __nv_bfloat16 *fqkv = nullptr, *f1 = nullptr;
   const float *c1q = nullptr, *c2q = nullptr, *c1f = nullptr, *c2f = nullptr;
   CUtensorMap tmf_wqkv, tmf_w1;                      // box = 128 rows
+  // QKV projection with the attention in its epilogue (qkv_attn.cuh): the folded Wqkv with its rows regrouped per head
+  const __nv_bfloat16* fqkv_h = nullptr;
+  const float *c1qh = nullptr, *c2qh = nullptr;
+  CUtensorMap tmh_wqkv;                              // box = 96 rows
 };
 
 struct owc_encoder {
@@ -133,6 +139,9 @@ struct owc_encoder {
   CUtensorMap tmf_qkv, tmf_o, tmf_1, tmf_2;
   bool wide = false;               // every GEMM width is a multiple of 256 (mpnet-base: 2304 / 768 / 3072): 256-column tiles
   bool wide_ln = false;            // the deferred-LayerNorm path is set up (wide && ctx->wide)
+  bool qkv_attn = false;           // ... and the fused QKV + attention kernel (head_dim 64)
+  __nv_bfloat16* wfold16h = nullptr;  // per-head regrouped folded Wqkv of every layer
+  float* wfold32h = nullptr;          // c1qh | c2qh of every layer
   __nv_bfloat16* wfold16 = nullptr;   // gamma-folded Wqkv | W1 of every layer
   float* wfold32 = nullptr;           // c1q | c2q | c1f | c2f of every layer
   float *st1 = nullptr, *st2 = nullptr;   // [slots][cap][2] partial row (sum, sumsq) after the attention block / the feed-forward block
@@ -409,6 +418,27 @@ static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap
   return check_launch(c, "k_gemm_wide");
 }
 
+// QKV projection + attention of one layer on a chunk (qkv_attn.cuh). d_blk: the chunk's row-block table on the device.
+static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
+  owc_ctx* c = e->ctx;
+  OWC_TRY(ensure_smem_attr(c, k_qkv_attn, qa::SMEM_BYTES));
+  const int n_items = (g.n_blk + 1) / 2;
+  const int clusters = std::max(1, std::min(n_items, c->sm_count / 2));
+  ProfScope prof(c, OWC_KCAT_GEMM, OWC_KCAT_GEMM_QKV);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = qa::SMEM_BYTES;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn, e->tm_xb, L.tmh_wqkv, g));
+  return check_launch(c, "k_qkv_attn");
+}
+
 template <int EPF>
 static int launch_gemm_f32(owc_ctx* c, const float* A, const float* W, const float* bias, const float* res, float* out,
                            int M, int N, int K, int ldo) {
@@ -474,6 +504,7 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (const char* wd2 = getenv("OWC_WIDE_DEEP")) c->wide_deep = atoi(wd2) != 0;
   if (const char* wr = getenv("OWC_WIDE_ROT")) c->wide_rot = atoi(wr) != 0;
   if (const char* fs = getenv("OWC_WIDE_FFN2_SPLIT")) c->wide_ffn2_split = atoi(fs) != 0;
+  if (const char* qa_ = getenv("OWC_QKV_ATTN")) c->qkv_attn = atoi(qa_) != 0;
   const bool want_wide_dbg = getenv("OWC_WIDE_DBG") && atoi(getenv("OWC_WIDE_DBG")) != 0;
   c->chunk_default = chunk_tokens <= 0;
   c->chunk_tokens = chunk_tokens > 0 ? std::max(1024, (chunk_tokens + 127) / 128 * 128) : c->sm_count * 128;
@@ -602,7 +633,7 @@ extern "C" int32_t owc_encoder_destroy(owc_encoder* e) {
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
   void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32,
-                  e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg, e->wfold16, e->wfold32, e->st1, e->st2};
+                  e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg, e->wfold16, e->wfold32, e->st1, e->st2, e->wfold16h, e->wfold32h};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -734,6 +765,24 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
           const_cast<float*>(Lw.c1f), const_cast<float*>(Lw.c2f));
       if (check_launch(c, "k_fold_weight")) { owc_encoder_destroy(e); return 1; }
       if (make_tmap(c, &Lw.tmf_wqkv, Lw.fqkv, 3 * h, h, 128) || make_tmap(c, &Lw.tmf_w1, Lw.f1, I, h, 128)) { owc_encoder_destroy(e); return 1; }
+    }
+    e->qkv_attn = hd == qa::D;
+    if (e->qkv_attn) {
+      LOAD_CU(cudaMalloc(&e->wfold16h, L * 3 * h * h * sizeof(__nv_bfloat16)));
+      LOAD_CU(cudaMalloc(&e->wfold32h, L * 2 * 3 * h * sizeof(float)));
+      for (size_t l = 0; l < L; ++l) {
+        LayerW& Lw = e->layers[l];
+        const float* g_in = l == 0 ? e->emb_g : e->layers[l - 1].ln2g;
+        const float* b_in = l == 0 ? e->emb_b : e->layers[l - 1].ln2b;
+        Lw.fqkv_h = e->wfold16h + l * 3 * h * h;
+        Lw.c1qh = e->wfold32h + l * 6 * h;
+        Lw.c2qh = Lw.c1qh + 3 * h;
+        k_fold_weight_heads<<<static_cast<unsigned>((3 * h + 7) / 8), 256, 0, c->stream>>>(
+            Lw.wqkv32, g_in, b_in, Lw.bqkv, static_cast<int>(h), a.heads, const_cast<__nv_bfloat16*>(Lw.fqkv_h),
+            const_cast<float*>(Lw.c1qh), const_cast<float*>(Lw.c2qh));
+        if (check_launch(c, "k_fold_weight_heads")) { owc_encoder_destroy(e); return 1; }
+        if (make_tmap(c, &Lw.tmh_wqkv, Lw.fqkv_h, 3 * h, h, qa::BN / 2)) { owc_encoder_destroy(e); return 1; }
+      }
     }
   }
   // ---- block-resident fused encoder: MiniLM-width BERT only (enc_fused.cuh) ----
@@ -1017,7 +1066,30 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
   aa.scale = 1.0f / sqrtf(static_cast<float>(H / a.heads));
   aa.rel_lut = e->rel_lut; aa.max_pos = a.max_pos;
   aa.qkv = e->qkv; aa.out = e->ao;
-  if (max_t <= 64 && c->attn_grp) {
+  const bool fuse_attn = e->qkv_attn && c->qkv_attn && max_t <= 64;
+  const void* d_blk = nullptr;
+  int n_blk = 0;
+  if (fuse_attn) {
+    // row blocks of whole sequences (<= 128 tokens, <= 128 sequences), greedy in sequence order, as for the block-resident encoder
+    std::vector<int32_t> blk;
+    blk.reserve(static_cast<size_t>(M) / 96 + 2);
+    blk.push_back(seq0);
+    int rows = 0, cnt = 0;
+    for (int s = seq0; s < seq0 + n_seq; ++s) {
+      const int len = cu[s + 1] - cu[s];
+      if (rows + len > 128 || cnt == 128) {
+        blk.push_back(s);
+        rows = 0;
+        cnt = 0;
+      }
+      rows += len;
+      ++cnt;
+    }
+    blk.push_back(seq0 + n_seq);
+    n_blk = static_cast<int>(blk.size()) - 1;
+    OWC_TRY(to_device(c, c->blk, blk.data(), blk.size() * sizeof(int32_t), OWC_MEM_HOST, &d_blk));
+  }
+  if (!fuse_attn && max_t <= 64 && c->attn_grp) {
     // attention groups: runs of consecutive sequences with at most 16 tokens together share one 16 x 16 tile; a longer
     // sequence is a group of its own
     std::vector<int32_t> grp;
@@ -1051,10 +1123,21 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
     WideArgs g{};
     g.M = M; g.N = 3 * H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
     g.c1 = L.c1q; g.c2 = L.c2q; g.stats_in = e->st2; g.slots_in = slots2;
-    OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g, OWC_KCAT_GEMM_QKV));
-    if (aa.grp != nullptr) OWC_TRY(launch_attn_grp(e, aa));
-    else if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
-    else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
+    if (fuse_attn) {
+      QkvAttnArgs qa_args{};
+      qa_args.n_blk = n_blk; qa_args.blk_seq = static_cast<const int32_t*>(d_blk); qa_args.cu = d_cu; qa_args.tok0 = tok0;
+      qa_args.M = M; qa_args.K = H; qa_args.heads = a.heads;
+      qa_args.c1 = L.c1qh; qa_args.c2 = L.c2qh; qa_args.stats_in = e->st2; qa_args.slots_in = slots2; qa_args.stat_stride = stride;
+      qa_args.inv_h = 1.0f / static_cast<float>(H); qa_args.ln_eps = a.ln_eps;
+      qa_args.ao = e->ao; qa_args.ldo = H;
+      qa_args.scale_log2 = aa.scale * 1.4426950408889634f; qa_args.rel_lut = e->rel_lut; qa_args.max_pos = a.max_pos;
+      OWC_TRY(launch_qkv_attn(e, L, qa_args));
+    } else {
+      OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g, OWC_KCAT_GEMM_QKV));
+      if (aa.grp != nullptr) OWC_TRY(launch_attn_grp(e, aa));
+      else if (aa.max_t <= 64) OWC_TRY(launch_attn_mma(e, aa));
+      else OWC_TRY(launch_attn<__nv_bfloat16>(e, aa));
+    }
     g = WideArgs{};
     g.M = M; g.N = H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
     g.bias = L.bo; g.y = e->x; g.stats_prev = e->st2; g.slots_in = slots2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;

@@ -294,3 +294,36 @@ def test_two_contexts_in_one_process_share_nothing(minilm):
     finally:
         e1.close()
         e2.close()
+
+
+@pytest.mark.parametrize("seed,lo,hi", [(0, 1, 65), (1, 1, 9), (2, 30, 65), (3, 60, 65), (4, 1, 3), (5, 14, 20)])
+def test_qkv_attention_kernel_on_ragged_lengths(mpnet, monkeypatch, seed, lo, hi):
+    """The QKV projection with the attention in its epilogue (qkv_attn.cuh): row blocks of whole sequences, several
+    short sequences per 16 x 16 tile, 32- and 64-row tiles for longer ones, block boundaries anywhere. Against the
+    separate-kernel path (same bf16 operands: tight) and the oracle; bit-identical run to run."""
+    b = mpnet
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(lo, hi, size=int(30000 / ((lo + hi) / 2)))
+    ids = rng.integers(5, b.arch.vocab - 1, size=int(lens.sum())).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    fused = Engine(b.arch, b.sd, device=0)
+    monkeypatch.setenv("OWC_QKV_ATTN", "0")
+    split = Engine(b.arch, b.sd, device=0)
+    try:
+        s0 = fused.stats()["kernel_launches"]
+        z1 = fused.encode(ids, cu)
+        assert fused.stats()["kernel_launches"] - s0 == 2 + 4 * b.arch.layers       # embed + 12 x (QKV+attn, O, FFN1, FFN2) + pool
+        assert np.isfinite(z1).all() and np.array_equal(z1, fused.encode(ids, cu))
+        z0 = split.encode(ids, cu)
+        assert np.abs(z1 - z0).max() < 2e-3
+        n = 96
+        pad = np.full((n, int(lens[:n].max())), b.arch.pad_id, np.int64)
+        mask = np.zeros_like(pad)
+        for i in range(n):
+            pad[i, :lens[i]] = ids[cu[i]:cu[i + 1]]
+            mask[i, :lens[i]] = 1
+        want = encoder_ref.encode_padded(b.sd, b.arch, torch.from_numpy(pad), torch.from_numpy(mask)).numpy()
+        assert np.abs(z1[:n] - want).max() < 1e-3
+    finally:
+        fused.close()
+        split.close()
