@@ -484,11 +484,30 @@ def measure_rows(name: str, rows: int, d: Dist, steps: int, warmup: int, flush, 
     wide = arch.hidden >= 768 and os.environ.get("OWC_WIDE", "1") != "0"
     gemm_ms = prof["gemm"]["ms"]
     kernel_flops = gemm_flops + (attn_flops if fused else 0.0)   # the fused kernel runs the attention inside the same launch
-    achieved = kernel_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
     shapes = ("gemm_qkv", "gemm_o", "gemm_ffn1", "gemm_ffn2")     # breakdown of "gemm" on the wide path: not added to totals
     total_ms = sum(v["ms"] for k, v in prof.items() if k not in shapes)
     n_launch = max(prof["gemm"]["launches"], 1)
+    # Wide path with the attention in the QKV projection's epilogue (k_qkv_attn, no attention launches): two kernels share
+    # the "gemm" bucket. The dominant one stays k_gemm_wide (O-projection, FFN1, FFN2); k_qkv_attn is reported beside it.
+    h_, i_ = arch.hidden, arch.inter
+    qkv_share = 3.0 * h_ * h_ / (4.0 * h_ * h_ + 2.0 * h_ * i_)
+    qkv_attn_fused = wide and prof["attn"]["launches"] == 0 and prof.get("gemm_qkv", {}).get("launches", 0) > 0
+    secondary = None
+    if qkv_attn_fused:
+        qkv_ms = prof["gemm_qkv"]["ms"]
+        q_flops = gemm_flops * qkv_share + attn_flops
+        secondary = {"kernel": "k_qkv_attn (QKV projection on tcgen05 with the deferred LayerNorm and the self-attention of the row block in its "
+                               "epilogue: q|k|v never reach HBM; the warp-level MMAs of the attention share the tensor pipe with the UMMAs)",
+                     "achieved": q_flops / (qkv_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": q_flops / (qkv_ms / 1e3) / 1e12 / peak if peak else None,
+                     "algorithmic_flops_per_launch": q_flops / max(prof["gemm_qkv"]["launches"], 1),
+                     "launches_per_step": prof["gemm_qkv"]["launches"], "avg_launch_ms": qkv_ms / max(prof["gemm_qkv"]["launches"], 1),
+                     "share_of_step": qkv_ms / total_ms if total_ms else None}
+        kernel_flops = gemm_flops * (1.0 - qkv_share)
+        gemm_ms -= qkv_ms
+        n_launch = max(n_launch - prof["gemm_qkv"]["launches"], 1)
+    achieved = kernel_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     traffic, tinfo = None, {}
     tpath = os.path.join(ROOT, "profiles", "r02_wide_traffic.json" if wide else "r01_fused_traffic.json")
     if (fused or wide) and os.path.exists(tpath):   # dram bytes per launch of the same kernel from the committed ncu --set full capture
@@ -497,6 +516,9 @@ def measure_rows(name: str, rows: int, d: Dist, steps: int, warmup: int, flush, 
         traffic = tinfo.get("bytes_per_launch")
     kname = ("k_encoder_fused (all encoder layers of a 256-row block pair per cluster in one launch: tcgen05 contractions, attention, GELU, LayerNorm)"
              if fused else
+             "k_gemm_wide (persistent CTA-pair tcgen05 contractions O-projection / FFN1 / FFN2 with the LayerNorms folded into their epilogues; "
+             "the QKV projection + attention kernel is under `secondary`)"
+             if qkv_attn_fused else
              "k_gemm_wide (persistent CTA-pair tcgen05 contractions QKV / O / FFN1 / FFN2 with the LayerNorms folded into their epilogues)"
              if wide else "k_gemm_tc (encoder QKV/O/FFN contractions, tcgen05)")
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -504,12 +526,17 @@ def measure_rows(name: str, rows: int, d: Dist, steps: int, warmup: int, flush, 
                 "traffic_source": (tinfo.get("launch") if traffic is not None else None),
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "scope": f"this rank's prediction shard ({wl.n_rows} rows, {wl.n_tok} tokens); the class-name launches are timed apart",
-                "algorithmic_flops_per_launch": kernel_flops / n_launch, "launches_per_step": prof["gemm"]["launches"],
+                "algorithmic_flops_per_launch": kernel_flops / n_launch, "launches_per_step": n_launch,
                 "avg_launch_ms": gemm_ms / n_launch, "share_of_step": gemm_ms / total_ms if total_ms else None,
                 "whole_step_tflops": (gemm_flops + attn_flops + 2.0 * wl.n_rows * len(wl.classes) * arch.hidden) / (total_ms / 1e3) / 1e12 if total_ms else None,
                 "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items() if k not in shapes or v["launches"]},
                 "class_names": {"launches": sum(v["launches"] for k, v in prof_cls.items() if k not in shapes),
                                 "ms": round(sum(v["ms"] for k, v in prof_cls.items() if k not in shapes), 4), "tokens": int(wl.ccu[-1])}}
+    if secondary is not None:
+        roofline["secondary"] = secondary
+        roofline["tensor_kernels_together"] = {"achieved": (gemm_flops + attn_flops) / (prof["gemm"]["ms"] / 1e3) / 1e12,
+                                               "frac": (gemm_flops + attn_flops) / (prof["gemm"]["ms"] / 1e3) / 1e12 / peak if peak else None,
+                                               "share_of_step": prof["gemm"]["ms"] / total_ms if total_ms else None}
     sim_ms = prof["sim_topk"]["ms"]
     sim_in_step = None
     if sim_ms > 0:

@@ -86,10 +86,10 @@ struct owc_ctx {
   int wide_rot = 0;        // clusters start their column-tile sweeps at different tiles (env OWC_WIDE_ROT=1; measured: QKV +5 %,
                            // the whole encode -1.5 % - the step is power-capped, not bound by any one kernel)
   int wide_ffn2_split = 1; // FFN2: the three column tiles of a row-block pair on three neighbouring clusters (env OWC_WIDE_FFN2_SPLIT)
-  int qkv_attn = 0;        // wide path: attention in the QKV projection's epilogue for sequences <= 64 tokens (env OWC_QKV_ATTN)
+  int qkv_attn = 1;        // wide path: attention in the QKV projection's epilogue for sequences <= 64 tokens (env OWC_QKV_ATTN)
   int wide_waves = 8;      // row-block pairs per cluster and chunk on that path (env OWC_WIDE_WAVES)
   std::map<const void*, size_t> smem_attr;   // kernels whose dynamic shared-memory opt-in was set on THIS device
-  long long* wide_dbg = nullptr;             // [32] cycle counters of the instrumented wide GEMM (env OWC_WIDE_DBG=1), else nullptr
+  long long* wide_dbg = nullptr;             // [48] cycle counters of the instrumented wide GEMM (env OWC_WIDE_DBG=1), else nullptr
   int sm_count = 0;
   EncodeTiledFn encode_tiled = nullptr;
   owc_stats stats{};
@@ -421,13 +421,15 @@ static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap
 // QKV projection + attention of one layer on a chunk (qkv_attn.cuh). d_blk: the chunk's row-block table on the device.
 static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
   owc_ctx* c = e->ctx;
-  OWC_TRY(ensure_smem_attr(c, k_qkv_attn, qa::SMEM_BYTES));
+  OWC_TRY(ensure_smem_attr(c, k_qkv_attn<false>, qa::SMEM_BYTES));
+  if (c->wide_dbg) OWC_TRY(ensure_smem_attr(c, k_qkv_attn<true>, qa::SMEM_BYTES));
+  g.dbg = c->wide_dbg ? c->wide_dbg + 32 : nullptr;
   const int n_items = (g.n_blk + 1) / 2;
   const int clusters = std::max(1, std::min(n_items, c->sm_count / 2));
   ProfScope prof(c, OWC_KCAT_GEMM, OWC_KCAT_GEMM_QKV);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(qa::THREADS);
   cfg.dynamicSmemBytes = qa::SMEM_BYTES;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
@@ -435,7 +437,8 @@ static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
   attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn, e->tm_xb, L.tmh_wqkv, g));
+  if (c->wide_dbg) CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn<true>, e->tm_xb, L.tmh_wqkv, g));
+  else CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn<false>, e->tm_xb, L.tmh_wqkv, g));
   return check_launch(c, "k_qkv_attn");
 }
 
@@ -525,8 +528,8 @@ extern "C" int32_t owc_ctx_create(int32_t device, void* stream, int32_t chunk_to
   if (cudaMalloc(&c->d_status, sizeof(int)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
   cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
   if (want_wide_dbg) {
-    if (cudaMalloc(&c->wide_dbg, 32 * sizeof(long long)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
-    cudaMemsetAsync(c->wide_dbg, 0, 32 * sizeof(long long), c->stream);
+    if (cudaMalloc(&c->wide_dbg, 48 * sizeof(long long)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
+    cudaMemsetAsync(c->wide_dbg, 0, 48 * sizeof(long long), c->stream);
   }
   *out = c;
   return 0;
@@ -766,7 +769,7 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
       if (check_launch(c, "k_fold_weight")) { owc_encoder_destroy(e); return 1; }
       if (make_tmap(c, &Lw.tmf_wqkv, Lw.fqkv, 3 * h, h, 128) || make_tmap(c, &Lw.tmf_w1, Lw.f1, I, h, 128)) { owc_encoder_destroy(e); return 1; }
     }
-    e->qkv_attn = hd == qa::D;
+    e->qkv_attn = hd == qa::D && a.heads <= qa::MAX_HEADS;
     if (e->qkv_attn) {
       LOAD_CU(cudaMalloc(&e->wfold16h, L * 3 * h * h * sizeof(__nv_bfloat16)));
       LOAD_CU(cudaMalloc(&e->wfold32h, L * 2 * 3 * h * sizeof(float)));
@@ -1707,8 +1710,8 @@ extern "C" int32_t owc_debug_wide_counters(owc_ctx* c, int64_t* out32, int32_t r
   if (!c || !out32) return fail("owc_debug_wide_counters: NULL argument");
   if (!c->wide_dbg) return fail("the ctx was not created with OWC_WIDE_DBG=1");
   CU_OK(cudaSetDevice(c->device));
-  CU_OK(cudaMemcpyAsync(out32, c->wide_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  if (reset) CU_OK(cudaMemsetAsync(c->wide_dbg, 0, 32 * sizeof(long long), c->stream));
+  CU_OK(cudaMemcpyAsync(out32, c->wide_dbg, 48 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  if (reset) CU_OK(cudaMemsetAsync(c->wide_dbg, 0, 48 * sizeof(long long), c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }

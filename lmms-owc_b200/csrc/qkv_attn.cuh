@@ -43,6 +43,7 @@ struct QkvAttnArgs {
   float scale_log2;          // head_dim^-0.5 * log2(e)
   const float* rel_lut;      // MPNet: [heads, 2 * max_pos - 1] bias by (k - q), or nullptr
   int max_pos;
+  long long* dbg;            // instrumented build: cycle counters (see k_qkv_attn), else unused
 };
 
 namespace qa {
@@ -52,12 +53,28 @@ constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int BH_BYTES = (BN / 2) * BK * 2; // 12 KB: this CTA's 96 rows of the head's weight tile
 constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-constexpr int STAGES = 6;
+constexpr int STAGES = 4;
+// Warp roles. The drain warps own one TMEM lane quadrant each (warp id % 4 selects the quadrant a warp may read); the
+// attention warps follow; the two single-lane issue roles take the TOP ids: the warp scheduler favours the highest warp id
+// of an SMSP and the other warps are busy, so on ids 0 / 1 the TMA / MMA issue loops starve (measured: 14.5 k clk per head
+// tile against 5.4 k clk of MMA work).
+constexpr int DRAIN_WARPS = 4;
+constexpr int ATT_WARPS = 10;                // 16 warps = 4 per scheduler: 128 registers per thread, the same as with 14
+constexpr int DRAIN_THREADS = DRAIN_WARPS * 32, ATT_THREADS = ATT_WARPS * 32;
+constexpr int W_TMA = DRAIN_WARPS + ATT_WARPS, W_MMA = W_TMA + 1;
+constexpr int THREADS = (W_MMA + 1) * 32;
+constexpr int MAX_HEADS = 12;               // the relative-position bias slices of every head live in shared memory
 constexpr int QROW = 3 * D * 2;             // 384 B per q|k|v row
-constexpr int QKV_BYTES = BM * QROW;        // 48 KB
+constexpr int QKV_BYTES = BM * QROW;        // 48 KB, twice: the rows of head h + 1 are written while head h is attended
 constexpr int OFF_QKV = STAGES * STAGE_BYTES;
-constexpr int OFF_TAIL = OFF_QKV + QKV_BYTES;
-constexpr int TAIL_BYTES = 512 /*barriers*/ + 544 /*seq_row*/ + 160 /*groups*/ + 2 * 2 * BN * 4 /*c1|c2, two parities*/;
+constexpr int OFF_TAIL = OFF_QKV + 2 * QKV_BYTES;
+constexpr int TBL_BYTES = 544 /*seq_row*/ + 144 /*grp_first*/ + 16 /*n_grp*/ + 256 /*row_rng*/;   // per item parity
+constexpr int OFF_TBL = 256 /*barriers, tmem slot*/;
+constexpr int OFF_PARAM = OFF_TBL + 2 * TBL_BYTES;               // c1 | c2 of one head, two parities: 3 KB
+constexpr int OFF_LUT = OFF_PARAM + 2 * 2 * BN * 4;              // bias slices: 6 KB
+constexpr int TAIL_BYTES = OFF_LUT + MAX_HEADS * 128 * 4;
+// With 200+ KB of shared memory the L1 keeps nothing: every __ldg in the epilogue is an L2 round trip (~800 clk), so what a
+// head tile needs is staged ahead of time (bias slices once per kernel, c1 | c2 one head ahead).
 constexpr int SMEM_BYTES = 1024 + OFF_TAIL + TAIL_BYTES;
 static_assert(SMEM_BYTES <= kSmemLimit, "shared memory budget");
 }  // namespace qa
@@ -71,11 +88,14 @@ __device__ __forceinline__ uint8_t* qa_chunk(uint8_t* qkv, int row, int c) {
 // One attention unit out of the shared q|k|v rows: a GROUP of consecutive sequences (<= 16 rows together, block-diagonal
 // mask; TP == 16) or one longer sequence (TP == 32 / 64). Rows [beg, beg + T) of the block. The output overwrites the unit's
 // own (dead) q chunks and is then copied out with 16-byte row-contiguous stores.
-template <int TP>
+template <int TP, bool DBG = false>
 __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const int* seq_row, int s_first, int s_last, int lane,
-                                          float scale_log2, const float* lut, __nv_bfloat16* out, int ldo) {
+                                          float scale_log2, const float* lut, __nv_bfloat16* out, int ldo, long long* ph = nullptr) {
   constexpr int NT = TP / 8, MT = TP / 16, DN = qa::D / 8;
   const int g = lane >> 2, t4 = lane & 3;
+  long long pc = 0;
+  if constexpr (DBG) pc = clock64();
+  auto stamp = [&](int k) { if constexpr (DBG) { const long long n = clock64(); ph[k] += n - pc; pc = n; } };
   auto row_of = [&](int i) { return min(beg + i, 127); };   // rows past the block are never used unmasked
   int lo = 0, hi = T;
   if (TP == 16) {   // key range of every tile row: lane r finds the sequence that owns row r
@@ -85,6 +105,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
       if (lane >= b && lane < e) { lo = b; hi = e; }
     }
   }
+  stamp(0);
 #pragma unroll 1
   for (int mt = 0; mt < MT; ++mt) {
     if (mt * 16 >= T) break;
@@ -119,6 +140,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
         }
       }
     }
+    stamp(1);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -129,7 +151,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
           const int i = (e < 2) ? r0 : r1;
           const bool ok = (e < 2) ? (j >= lo0 && j < hi0) : (j >= lo1 && j < hi1);
           float v = s[nt][e] * scale_log2;
-          if (lut != nullptr && ok) v += __ldg(lut + (j - i)) * 1.4426950408889634f;
+          if (lut != nullptr && ok) v += lut[j - i];   // shared memory, already in the log2 domain
           v = ok ? v : -INFINITY;
           s[nt][e] = v;
           if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
@@ -167,6 +189,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    stamp(2);
     float o[DN][4];
 #pragma unroll
     for (int dn = 0; dn < DN; ++dn) { o[dn][0] = 0.f; o[dn][1] = 0.f; o[dn][2] = 0.f; o[dn][3] = 0.f; }
@@ -187,6 +210,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(fmaxf(sum0, 1.0f)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(fmaxf(sum1, 1.0f)));
     __syncwarp();   // every lane has read this m-tile's q rows
+    stamp(3);
 #pragma unroll
     for (int dn = 0; dn < DN; ++dn) {
       if (r0 < T) *reinterpret_cast<uint32_t*>(qa_chunk(qkv, beg + r0, dn) + t4 * 4) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
@@ -194,14 +218,154 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
     }
   }
   __syncwarp();
+  stamp(4);
   // 16-byte, row-contiguous write-back: 8 lanes cover one 128-byte output row segment
   for (int idx = lane; idx < T * 8; idx += 32) {
     const int c = idx & 7, t = idx >> 3;
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(beg + t) * ldo + c * 8) = *reinterpret_cast<const uint4*>(qa_chunk(qkv, beg + t, c));
   }
+  stamp(5);
+  if constexpr (DBG) ph[6] += 1;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// D = A B with a zero accumulator (an independent instruction: nothing to wait for but its operands)
+__device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+// The hot case: a group of consecutive sequences with <= 16 rows together, one 16 x 16 score tile. mma.sync shares the tensor
+// core with the kernel's tcgen05 stream and queues behind the UMMAs in flight: a DEPENDENT warp-level MMA costs ~700 clk here
+// (measured: 2.9 k clk for the four chained k-steps of a 16 x 16 x 64 score tile). So every MMA of a phase is independent -
+// the k-steps of Q K^T accumulate into separate registers that are summed afterwards - and the unit waits on the tensor core
+// twice (scores, P V) instead of five times; all fragments come in by ldmatrix.x4 before the first MMA.
+// row_rng[r] = first | (end << 8) of the block-relative key range of row r's sequence.
+template <bool DBG>
+__device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const uint16_t* row_rng, int lane, float scale_log2,
+                                            const float* lut, __nv_bfloat16* out, int ldo, long long* ph) {
+  const int g = lane >> 2, t4 = lane & 3;
+  long long pc = 0;
+  if constexpr (DBG) pc = clock64();
+  auto stamp = [&](int k) { if constexpr (DBG) { const long long n = clock64(); ph[k] += n - pc; pc = n; } };
+  const uint32_t base = smem_u32(qkv);
+  uint32_t qf[4][4], kf[4][4], vf[4][4];
+  {
+    const int qrow = min(beg + (lane & 7) + ((lane >> 3) & 1) * 8, 127), qhi = lane >> 4;
+    const int krow = min(beg + (lane & 7) + (lane >> 4) * 8, 127), khi = (lane >> 3) & 1;
+    const int vrow = min(beg + (lane & 15), 127), vhi = lane >> 4;
+    const uint32_t qb = base + qrow * qa::QROW, kb = base + krow * qa::QROW + 128, vb = base + vrow * qa::QROW + 256;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      ldmatrix_x4(qf[ks], qb + (((2 * ks + qhi) ^ (qrow & 7)) << 4));
+      ldmatrix_x4(kf[ks], kb + (((2 * ks + khi) ^ (krow & 7)) << 4));
+    }
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) ldmatrix_x4_trans(vf[dp], vb + (((2 * dp + vhi) ^ (vrow & 7)) << 4));
+  }
+  // key ranges of this lane's two rows (unit-relative); rows past the unit see no key
+  const int r0 = g, r1 = g + 8;
+  int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  if (r0 < T) { const int v = row_rng[beg + r0]; lo0 = (v & 0xff) - beg; hi0 = (v >> 8) - beg; }
+  if (r1 < T) { const int v = row_rng[beg + r1]; lo1 = (v & 0xff) - beg; hi1 = (v >> 8) - beg; }
+  stamp(0);
+  float sp[4][2][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    mma_bf16_16816_z(sp[ks][0], qf[ks], kf[ks][0], kf[ks][1]);
+    mma_bf16_16816_z(sp[ks][1], qf[ks], kf[ks][2], kf[ks][3]);
+  }
+  float s[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[nt][e] = (sp[0][nt][e] + sp[1][nt][e]) + (sp[2][nt][e] + sp[3][nt][e]);
+  stamp(1);
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = nt * 8 + t4 * 2 + (e & 1);
+      const int i = (e < 2) ? r0 : r1;
+      const bool ok = (e < 2) ? (j >= lo0 && j < hi0) : (j >= lo1 && j < hi1);
+      float v = s[nt][e] * scale_log2;
+      if (lut != nullptr && ok) v += lut[j - i];   // shared memory, already in the log2 domain
+      v = ok ? v : -INFINITY;
+      s[nt][e] = v;
+      if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  m0 = (hi0 > lo0) ? m0 : 0.f;   // tile rows without a key: keep (-inf) - (-inf) out of the exponent
+  m1 = (hi1 > lo1) ? m1 : 0.f;
+  uint32_t pk[2][2];
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    float e0, e1, e2, e3;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s[nt][0] - m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s[nt][1] - m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(s[nt][2] - m1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(s[nt][3] - m1));
+    const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+    const __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+    sum0 += __low2float(p01) + __high2float(p01);
+    sum1 += __low2float(p23) + __high2float(p23);
+    pk[nt][0] = *reinterpret_cast<const uint32_t*>(&p01);
+    pk[nt][1] = *reinterpret_cast<const uint32_t*>(&p23);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  stamp(2);
+  const uint32_t af[4] = {pk[0][0], pk[0][1], pk[1][0], pk[1][1]};
+  float o[8][4];
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) mma_bf16_16816_z(o[dn], af, vf[dn >> 1][(dn & 1) * 2], vf[dn >> 1][(dn & 1) * 2 + 1]);
+  float inv0, inv1;   // real rows sum to >= 1 (the row maximum contributes 2^0); rows without keys are not stored
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(fmaxf(sum0, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(fmaxf(sum1, 1.0f)));
+  __syncwarp();   // every lane has read the unit's q rows
+  stamp(3);
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    if (r0 < T) *reinterpret_cast<uint32_t*>(qa_chunk(qkv, beg + r0, dn) + t4 * 4) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(qa_chunk(qkv, beg + r1, dn) + t4 * 4) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+  }
+  __syncwarp();
+  stamp(4);
+  // 16-byte, row-contiguous write-back: 8 lanes cover one 128-byte output row segment
+  for (int idx = lane; idx < T * 8; idx += 32) {
+    const int c = idx & 7, t = idx >> 3;
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(beg + t) * ldo + c * 8) = *reinterpret_cast<const uint4*>(qa_chunk(qkv, beg + t, c));
+  }
+  stamp(5);
+  if constexpr (DBG) ph[6] += 1;
+}
+
+
+// Cycle counters of the instrumented build (g.dbg, leader CTAs only, accumulated with atomics):
+//   [0] MMA warp: ring wait  [1] accumulator wait  [2] MMA warp total  [3] drain warp 0: accumulator (tfull) wait
+//   [4] drain warp 0: q|k|v buffer wait  [5] drain warp 0 total  [6] CTAs  [8] attention warp 0: q|k|v rows wait
+//   [9] attention warp 0: table building  [10] attention warp 0 total  [11..15] its phases of qa_attend: tile bounds, QK,
+//   softmax, PV, rows to shared memory (the write-back is the rest)  [7] attention units of warp 0
+template <bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(qa::THREADS, 1)
 k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QkvAttnArgs g) {
   using namespace qa;
   extern __shared__ uint8_t smem_raw[];
@@ -210,13 +374,13 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint8_t* tail = tiles + OFF_TAIL;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  int* seq_row = reinterpret_cast<int*>(tail + 512);            // [<= 130] first row (block-relative) of each sequence
-  uint8_t* grp_first = tail + 512 + 544;                        // [n_grp + 1] first sequence of each attention group
-  int* n_grp_s = reinterpret_cast<int*>(tail + 512 + 544 + 144);
-  float* param_s = reinterpret_cast<float*>(tail + 512 + 544 + 160);   // [2][c1 | c2][BN]
+  uint64_t* tfull = empty + STAGES;       // accumulator complete (MMA -> drain warps of both CTAs)
+  uint64_t* tempty = tfull + 2;           // accumulator drained (drain warps of both CTAs -> leader's MMA warp)
+  uint64_t* qfull = tempty + 2;           // q|k|v rows of a head in shared memory (drain warps -> attention warps)
+  uint64_t* qfree = qfull + 2;            // ... and read for the last time (attention warps -> drain warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfree + 2);
+  float* param_s = reinterpret_cast<float*>(tail + OFF_PARAM);         // [2][c1 | c2][BN]
+  float* lut_s = reinterpret_cast<float*>(tail + OFF_LUT);             // [heads][128]: bias of offset d at [h][d + 63], log2 domain
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -227,14 +391,19 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   const int n_items = (g.n_blk + 1) >> 1;
   const int num_kb = g.K / BK;
 
-  if (warp == 1 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * kEpiWarps); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 2 * DRAIN_WARPS);
+      mbar_init(&qfull[b], DRAIN_WARPS);
+      mbar_init(&qfree[b], ATT_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == W_TMA) {
     tmem_alloc_2sm(tmem_slot, 512);
     tmem_relinquish_2sm();
   }
@@ -248,7 +417,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   // first token row of this CTA's block of item `it`; a missing odd tail block re-reads the leader's rows (never stored)
   auto block_of = [&](int it) { return min(2 * it + static_cast<int>(rank), g.n_blk - 1); };
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       int stage = 0;
@@ -268,7 +437,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     if (leader) {
       // ---------------- MMA issuer: UMMA 256 x 192 x 16 across the pair ----------------
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
@@ -276,14 +445,20 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int stage = 0;
       uint32_t phase = 0;
       uint32_t t = 0;
+      long long w_ring = 0, w_acc = 0, t_begin = 0, c0 = 0;
+      if constexpr (DBG) t_begin = clock64();
       for (int it = cluster_id; it < n_items; it += n_clusters) {
         for (int h = 0; h < g.heads; ++h, ++t) {
           const uint32_t buf = t & 1u;
+          if constexpr (DBG) c0 = clock64();
           mbar_wait(&tempty[buf], ((t >> 1) & 1u) ^ 1u);
+          if constexpr (DBG) w_acc += clock64() - c0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
+            if constexpr (DBG) c0 = clock64();
             mbar_wait(&full[stage], phase);
+            if constexpr (DBG) w_ring += clock64() - c0;
             tc_fence_after();
             const uint32_t a_lo = tiles_lo + static_cast<uint32_t>(stage * (STAGE_BYTES >> 4));
             if (elect_one_sync()) {
@@ -297,38 +472,39 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           __syncwarp();
         }
       }
-    }
-  } else {
-    // ---------------- epilogue warps: deferred LayerNorm, q|k|v rows to shared memory, attention, output rows ----------------
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int we = warp - 2;                    // 0..7
-    const int et = threadIdx.x - 64;
-    const int r = q * 32 + lane;                // token row of this thread inside the block
-    uint32_t t = 0;
-    for (int it = cluster_id; it < n_items; it += n_clusters) {
-      const int blk = 2 * it + static_cast<int>(rank);
-      const bool have = blk < g.n_blk;
-      const int s0 = __ldg(g.blk_seq + block_of(it));
-      const int nseq = have ? __ldg(g.blk_seq + blk + 1) - s0 : 0;
-      const int row0 = __ldg(g.cu + s0) - g.tok0;
-      named_bar_sync(1, kEpiThreads);           // everyone is done with the previous block's tables
-      for (int i = et; i <= nseq; i += kEpiThreads) seq_row[i] = __ldg(g.cu + s0 + i) - g.tok0 - row0;
-      named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
-        int ng = 0, rows = 0;
-        grp_first[0] = 0;
-        for (int i = 0; i < nseq; ++i) {
-          const int len = seq_row[i + 1] - seq_row[i];
-          if (rows > 0 && rows + len > 16) {
-            grp_first[++ng] = static_cast<uint8_t>(i);
-            rows = 0;
-          }
-          rows += len;
+      if constexpr (DBG) {
+        if (lane == 0 && g.dbg != nullptr) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 0), static_cast<unsigned long long>(w_ring));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 1), static_cast<unsigned long long>(w_acc));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 2), static_cast<unsigned long long>(clock64() - t_begin));
+          atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 6), 1ull);
         }
-        if (nseq > 0) grp_first[++ng] = static_cast<uint8_t>(nseq);
-        *n_grp_s = ng;
       }
+    }
+  } else if (warp < DRAIN_WARPS) {
+    // ---------------- drain warps: accumulator -> deferred LayerNorm -> bf16 q|k|v rows in shared memory ----------------
+    const int r = warp * 32 + lane;             // token row of this thread inside the block = its TMEM lane
+    const int dt = threadIdx.x;                 // 0..127
+    // c1 | c2 of a head: 384 floats, three per thread, fetched one head ahead (the L2 round trip hides behind the waits)
+    auto ld_params = [&](int h, float (&p)[3]) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int idx = dt + i * DRAIN_THREADS;
+        p[i] = idx < BN ? __ldg(g.c1 + h * BN + idx) : __ldg(g.c2 + h * BN + idx - BN);
+      }
+    };
+    {
+      float p[3];
+      ld_params(0, p);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) param_s[dt + i * DRAIN_THREADS] = p[i];
+    }
+    named_bar_sync(3, DRAIN_THREADS);
+    uint32_t t = 0;
+    long long w_tfull = 0, w_qfree = 0, e_begin = 0, c0 = 0;
+    if constexpr (DBG) e_begin = clock64();
+    for (int it = cluster_id; it < n_items; it += n_clusters) {
+      const int row0 = __ldg(g.cu + __ldg(g.blk_seq + block_of(it))) - g.tok0;
       // per-row LayerNorm of the incoming stream: x = y * ra + rb
       float ra = 0.f, rb = 0.f;
       {
@@ -348,24 +524,26 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
       for (int h = 0; h < g.heads; ++h, ++t) {
         const uint32_t buf = t & 1u;
-        float* p0 = param_s + buf * 2 * BN;
-        if (et < BN) {
-          p0[et] = __ldg(g.c1 + h * BN + et);
-          p0[BN + et] = __ldg(g.c2 + h * BN + et);
-        }
-        named_bar_sync(1, kEpiThreads);         // parameters staged; the attention of the previous head has left the q|k|v rows
-        mbar_wait(&tfull[buf], (t >> 1) & 1u);
+        const uint32_t par = (t >> 1) & 1u;
+        const float* p0 = param_s + buf * 2 * BN;
+        float pn[3];
+        ld_params(h + 1 < g.heads ? h + 1 : 0, pn);
+        if constexpr (DBG) c0 = clock64();
+        mbar_wait(&qfree[buf], par ^ 1u);       // the attention of head t - 2 has left this q|k|v buffer
+        if constexpr (DBG) { const long long c1 = clock64(); w_qfree += c1 - c0; c0 = c1; }
+        mbar_wait(&tfull[buf], par);
+        if constexpr (DBG) w_tfull += clock64() - c0;
         tc_fence_after();
-        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-        // this warp's three 32-column chunks of the head tile: chunk c = 2 * cw + half (q: 0,1  k: 2,3  v: 4,5)
+        uint8_t* qb = qkv_s + buf * QKV_BYTES;
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * BN;
+        // six 32-column chunks of the head tile (q: 0,1  k: 2,3  v: 4,5), the next one in flight while one is converted
         uint32_t v[2][32];
-        tmem_ld_32x32(tbase + static_cast<uint32_t>(half * 32), v[0]);
+        tmem_ld_32x32(tbase, v[0]);
 #pragma unroll
-        for (int cw = 0; cw < 3; ++cw) {
-          const int c = 2 * cw + half;
-          tmem_ld_wait_dep(v[cw & 1]);
-          if (cw + 1 < 3) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 2) * 32), v[(cw + 1) & 1]);
-          const uint32_t (&vc)[32] = v[cw & 1];
+        for (int c = 0; c < 6; ++c) {
+          tmem_ld_wait_dep(v[c & 1]);
+          if (c + 1 < 6) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 1) * 32), v[(c + 1) & 1]);
+          const uint32_t (&vc)[32] = v[c & 1];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {         // four 16-byte chunks of 8 columns
             const float4 k1a = *reinterpret_cast<const float4*>(p0 + c * 32 + 8 * j);
@@ -381,33 +559,112 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                               fmaf(__uint_as_float(vc[8 * j + 5]), ra, fmaf(rb, k1b.y, k2b.y)));
             w.w = pack_bf16x2(fmaf(__uint_as_float(vc[8 * j + 6]), ra, fmaf(rb, k1b.z, k2b.z)),
                               fmaf(__uint_as_float(vc[8 * j + 7]), ra, fmaf(rb, k1b.w, k2b.w)));
-            *reinterpret_cast<uint4*>(qa_chunk(qkv_s, r, c * 4 + j)) = w;
+            *reinterpret_cast<uint4*>(qa_chunk(qb, r, c * 4 + j)) = w;
           }
         }
         tc_fence_before();
+        float* pw = param_s + (buf ^ 1u) * 2 * BN;   // last read during head t - 1, which every drain warp has left
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pw[dt + i * DRAIN_THREADS] = pn[i];
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));   // accumulator drained: the MMAs of head h+2 may start
-        named_bar_sync(2, kEpiThreads);         // every row of the head is in shared memory
-        // ---- attention of the block's sequences for this head (unit u -> epilogue warp u % 8) ----
-        const int n_grp = *n_grp_s;
-        const float* lut = g.rel_lut ? g.rel_lut + static_cast<size_t>(h) * (2 * g.max_pos - 1) + g.max_pos - 1 : nullptr;
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));   // accumulator drained: the MMAs of head t + 2 may start
+          mbar_arrive(&qfull[buf]);                                   // this warp's 32 rows of the head are in shared memory
+        }
+        named_bar_sync(3, DRAIN_THREADS);       // the next head's parameters are staged
+      }
+    }
+    if constexpr (DBG) {
+      if (warp == 0 && lane == 0 && leader && g.dbg != nullptr) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 3), static_cast<unsigned long long>(w_tfull));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 4), static_cast<unsigned long long>(w_qfree));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 5), static_cast<unsigned long long>(clock64() - e_begin));
+      }
+    }
+  } else {
+    // ---------------- attention warps: the block's sequences, head by head, out of the shared q|k|v rows ----------------
+    const int aw = warp - DRAIN_WARPS;
+    const int at = threadIdx.x - DRAIN_THREADS;
+    for (int i = at; i < g.heads * 128; i += ATT_THREADS) {
+      const int h = i >> 7, d = (i & 127) - 63;
+      lut_s[i] = (g.rel_lut != nullptr && d <= 63) ? __ldg(g.rel_lut + static_cast<size_t>(h) * (2 * g.max_pos - 1) + g.max_pos - 1 + d) * 1.4426950408889634f : 0.f;
+    }
+    uint32_t t = 0;
+    uint32_t ip = 0;                            // item parity: the tables of item i + 1 are built while stragglers read item i's
+    long long w_qfull = 0, w_tbl = 0, a_begin = 0, c0 = 0;
+    long long ph[7] = {0, 0, 0, 0, 0, 0, 0};   // DBG: phases of qa_attend (tile bounds, QK, softmax, PV, rows to shared, write-back), units
+    if constexpr (DBG) a_begin = clock64();
+    for (int it = cluster_id; it < n_items; it += n_clusters, ip ^= 1u) {
+      if constexpr (DBG) c0 = clock64();
+      uint8_t* tbl = tail + OFF_TBL + ip * TBL_BYTES;
+      int* seq_row = reinterpret_cast<int*>(tbl);                  // [<= 130] first row (block-relative) of each sequence
+      uint8_t* grp_first = tbl + 544;                              // [n_grp + 1] first sequence of each attention group
+      int* n_grp_s = reinterpret_cast<int*>(tbl + 544 + 144);
+      uint16_t* row_rng = reinterpret_cast<uint16_t*>(tbl + 544 + 144 + 16);   // [128] key range of each row's sequence
+      const int blk = 2 * it + static_cast<int>(rank);
+      const bool have = blk < g.n_blk;
+      const int s0 = __ldg(g.blk_seq + block_of(it));
+      const int nseq = have ? __ldg(g.blk_seq + blk + 1) - s0 : 0;
+      const int row0 = __ldg(g.cu + s0) - g.tok0;
+      for (int i = at; i <= nseq; i += ATT_THREADS) seq_row[i] = __ldg(g.cu + s0 + i) - g.tok0 - row0;
+      named_bar_sync(1, ATT_THREADS);
+      if (at == 0) {
+        int ng = 0, rows = 0;
+        grp_first[0] = 0;
+        for (int i = 0; i < nseq; ++i) {
+          const int len = seq_row[i + 1] - seq_row[i];
+          if (rows > 0 && rows + len > 16) {
+            grp_first[++ng] = static_cast<uint8_t>(i);
+            rows = 0;
+          }
+          rows += len;
+        }
+        if (nseq > 0) grp_first[++ng] = static_cast<uint8_t>(nseq);
+        *n_grp_s = ng;
+      }
+      for (int i = ATT_THREADS - 1 - at; i < nseq; i += ATT_THREADS) {   // thread 0 is busy with the groups
+        const int b = seq_row[i], e = seq_row[i + 1];
+        for (int rr = b; rr < e; ++rr) row_rng[rr] = static_cast<uint16_t>(b | (e << 8));
+      }
+      named_bar_sync(1, ATT_THREADS);
+      if constexpr (DBG) w_tbl += clock64() - c0;
+      const int n_grp = *n_grp_s;
+      for (int h = 0; h < g.heads; ++h, ++t) {
+        const uint32_t buf = t & 1u;
+        if constexpr (DBG) c0 = clock64();
+        mbar_wait(&qfull[buf], (t >> 1) & 1u);
+        if constexpr (DBG) w_qfull += clock64() - c0;
+        uint8_t* qb = qkv_s + buf * QKV_BYTES;
+        const float* lut = g.rel_lut ? lut_s + h * 128 + 63 : nullptr;
         __nv_bfloat16* out = g.ao + static_cast<size_t>(row0) * g.ldo + h * D;
-        for (int u = we; u < n_grp; u += kEpiWarps) {
+        for (int u = aw; u < n_grp; u += ATT_WARPS) {
           const int s_first = grp_first[u], s_last = grp_first[u + 1];
           const int beg = seq_row[s_first];
           const int T = seq_row[s_last] - beg;
           if (T <= 0) continue;
-          if (T <= 16) qa_attend<16>(qkv_s, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo);
-          else if (T <= 32) qa_attend<32>(qkv_s, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo);
-          else qa_attend<64>(qkv_s, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo);
+          if (T <= 16) qa_attend16<DBG>(qb, beg, T, row_rng, lane, g.scale_log2, lut, out, g.ldo, ph);
+          else if (T <= 32) qa_attend<32, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
+          else qa_attend<64, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qfree[buf]);
+      }
+    }
+    if constexpr (DBG) {
+      if (aw == 0 && lane == 0 && leader && g.dbg != nullptr) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 8), static_cast<unsigned long long>(w_qfull));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 9), static_cast<unsigned long long>(w_tbl));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 10), static_cast<unsigned long long>(clock64() - a_begin));
+        for (int k = 0; k < 5; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 11 + k), static_cast<unsigned long long>(ph[k]));
+        atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg + 7), static_cast<unsigned long long>(ph[6]));   // attention units of warp 0
+        // ph[5] (write-back) = attention total - waits - tables - the five phases above
       }
     }
   }
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 0) {
+  if (warp == W_TMA) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);

@@ -324,10 +324,11 @@ class Engine:
         return out
 
     def wide_counters(self, reset: bool = True) -> np.ndarray:
-        """Cycle counters of the instrumented wide GEMM (``OWC_WIDE_DBG=1``): ``[4, 8]`` int64, see owc_b200_debug.h."""
-        out = np.zeros(32, dtype=np.int64)
+        """Cycle counters of the instrumented wide GEMM (``OWC_WIDE_DBG=1``): ``[6, 8]`` int64 (rows 0-3: the four
+        epilogue kinds of ``k_gemm_wide``; rows 4-5: ``k_qkv_attn``), see owc_b200_debug.h."""
+        out = np.zeros(48, dtype=np.int64)
         _cabi.check(self._lib.owc_debug_wide_counters(self._ctx, out.ctypes.data, int(reset)))
-        return out.reshape(4, 8)
+        return out.reshape(6, 8)
 
     def bench_sim_kernel(self, n: int, c: int, dim: int, k: int, iters: int) -> float:
         ms = C.c_float(0.0)

@@ -306,6 +306,7 @@ def test_qkv_attention_kernel_on_ragged_lengths(mpnet, monkeypatch, seed, lo, hi
     lens = rng.integers(lo, hi, size=int(30000 / ((lo + hi) / 2)))
     ids = rng.integers(5, b.arch.vocab - 1, size=int(lens.sum())).astype(np.int32)
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    monkeypatch.setenv("OWC_QKV_ATTN", "1")
     fused = Engine(b.arch, b.sd, device=0)
     monkeypatch.setenv("OWC_QKV_ATTN", "0")
     split = Engine(b.arch, b.sd, device=0)

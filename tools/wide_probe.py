@@ -49,6 +49,18 @@ for waves in waves_list:
             c = eng.wide_counters()
             print(f"  instrumented build, OWC_WIDE_EXP={os.environ.get('OWC_WIDE_EXP', '0')}: " + ", ".join(
                 f"{k} {v['ms']:.2f} ms ({arch.layers * shape_flops[k] * n_tok / v['ms'] / 1e9:.0f} TF/s)" for k, v in prof.items() if k in shape_flops))
+            if c[4][2]:
+                ring, acc, tot, dtf, dqf, dtot, n = (int(x) for x in c[4][:7])
+                aqf, atbl, atot = (int(x) for x in c[5][:3])
+                units = max(int(c[4][7]), 1)
+                phs = [int(x) for x in c[5][3:8]]
+                print(f"  k_qkv_attn attention warp 0: {units} units, clk per unit: bounds {phs[0] / units:.0f}, QK {phs[1] / units:.0f}, softmax {phs[2] / units:.0f}, "
+                      f"PV {phs[3] / units:.0f}, rows to shared {phs[4] / units:.0f}, write-back + loop {(atot - aqf - atbl - sum(phs)) / units:.0f}", flush=True)
+                tiles = n_tok / 100.0   # only for scale
+                print(f"  k_qkv_attn: MMA warp ring wait {ring / tot:6.1%}  accumulator wait {acc / tot:6.1%}  issue {1 - (ring + acc) / tot:6.1%} | "
+                      f"drain warp 0: accumulator wait {dtf / dtot:6.1%}  q|k|v buffer wait {dqf / dtot:6.1%}  work {1 - (dtf + dqf) / dtot:6.1%} | "
+                      f"attention warp 0: rows wait {aqf / atot:6.1%}  tables {atbl / atot:6.1%}  work {1 - (aqf + atbl) / atot:6.1%} | "
+                      f"clk per leader CTA and launch {tot / max(n, 1):.0f} (leader CTAs x launches {n})", flush=True)
             for k, nm in enumerate(names):
                 ring, acc, tot, etf, etot, n = c[k][:6]
                 if tot:
