@@ -340,20 +340,18 @@ __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const 
   float inv0, inv1;   // real rows sum to >= 1 (the row maximum contributes 2^0); rows without keys are not stored
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(fmaxf(sum0, 1.0f)));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(fmaxf(sum1, 1.0f)));
-  __syncwarp();   // every lane has read the unit's q rows
   stamp(3);
+  // Straight from the fragments to global memory: lane (g, t4) owns columns 8 dn + 2 t4, + 1 of rows g and g + 8, so one
+  // store instruction covers 16 contiguous bytes of 8 rows. Staging the rows in shared memory for 16-byte stores put an
+  // STS -> bar -> LDS -> STG chain of ~3 k clk on the unit's critical path; the half-sector writes merge in L2.
+  __nv_bfloat16* o0 = out + static_cast<size_t>(beg + r0) * ldo + t4 * 2;
+  __nv_bfloat16* o1 = out + static_cast<size_t>(beg + r1) * ldo + t4 * 2;
 #pragma unroll
   for (int dn = 0; dn < 8; ++dn) {
-    if (r0 < T) *reinterpret_cast<uint32_t*>(qa_chunk(qkv, beg + r0, dn) + t4 * 4) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-    if (r1 < T) *reinterpret_cast<uint32_t*>(qa_chunk(qkv, beg + r1, dn) + t4 * 4) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+    if (r0 < T) *reinterpret_cast<uint32_t*>(o0 + dn * 8) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(o1 + dn * 8) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
   }
-  __syncwarp();
   stamp(4);
-  // 16-byte, row-contiguous write-back: 8 lanes cover one 128-byte output row segment
-  for (int idx = lane; idx < T * 8; idx += 32) {
-    const int c = idx & 7, t = idx >> 3;
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(beg + t) * ldo + c * 8) = *reinterpret_cast<const uint4*>(qa_chunk(qkv, beg + t, c));
-  }
   stamp(5);
   if constexpr (DBG) ph[6] += 1;
 }
