@@ -424,6 +424,9 @@ static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
   OWC_TRY(ensure_smem_attr(c, k_qkv_attn<false>, qa::SMEM_BYTES));
   if (c->wide_dbg) OWC_TRY(ensure_smem_attr(c, k_qkv_attn<true>, qa::SMEM_BYTES));
   g.dbg = c->wide_dbg ? c->wide_dbg + 32 : nullptr;
+  if (c->wide_dbg) {
+    if (const char* ex = getenv("OWC_WIDE_EXP")) g.exp = atoi(ex);   // instrumented build only (wrong results by construction)
+  }
   const int n_items = (g.n_blk + 1) / 2;
   const int clusters = std::max(1, std::min(n_items, c->sm_count / 2));
   ProfScope prof(c, OWC_KCAT_GEMM, OWC_KCAT_GEMM_QKV);

@@ -44,6 +44,7 @@ struct QkvAttnArgs {
   const float* rel_lut;      // MPNet: [heads, 2 * max_pos - 1] bias by (k - q), or nullptr
   int max_pos;
   long long* dbg;            // instrumented build: cycle counters (see k_qkv_attn), else unused
+  int exp;                   // instrumented build only, WRONG results: bit 1 = skip the attention of every unit (MMA + drain alone), bit 2 = issue no UMMA (TMA + drain + attention alone)
 };
 
 namespace qa {
@@ -460,7 +461,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             tc_fence_after();
             const uint32_t a_lo = tiles_lo + static_cast<uint32_t>(stage * (STAGE_BYTES >> 4));
             if (elect_one_sync()) {
-              umma_kblock_2sm(d_tmem, a_lo, a_lo + (A_BYTES >> 4), idesc, static_cast<uint32_t>(kb != 0));
+              if (!(DBG && (g.exp & 4))) umma_kblock_2sm(d_tmem, a_lo, a_lo + (A_BYTES >> 4), idesc, static_cast<uint32_t>(kb != 0));
               umma_commit_2sm(&empty[stage]);
             }
             __syncwarp();
@@ -640,6 +641,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const int beg = seq_row[s_first];
           const int T = seq_row[s_last] - beg;
           if (T <= 0) continue;
+          if (DBG && (g.exp & 2)) continue;
           if (T <= 16) qa_attend16<DBG>(qb, beg, T, row_rng, lane, g.scale_log2, lut, out, g.ldo, ph);
           else if (T <= 32) qa_attend<32, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
           else qa_attend<64, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
