@@ -44,6 +44,7 @@ struct QkvAttnArgs {
   const float* rel_lut;      // MPNet: [heads, 2 * max_pos - 1] bias by (k - q), or nullptr
   int max_pos;
   long long* dbg;            // instrumented build: cycle counters (see k_qkv_attn), else unused
+  int burst;                 // > 1: the MMA warp issues this many k-blocks back to back once the last of them has landed (env OWC_QKV_BURST)
   int exp;                   // instrumented build only, WRONG results: bit 1 = skip the attention of every unit (MMA + drain alone), bit 2 = issue no UMMA (TMA + drain + attention alone)
 };
 
@@ -456,6 +457,10 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
             if constexpr (DBG) c0 = clock64();
+            // Pairs of k-blocks go to the tensor pipe back to back, with a gap before the next pair: the warp-level MMAs of the
+            // attention queue behind UMMAs in flight (see qa_attend16) and get through in the gaps. One k-block at a time
+            // leaves no gap (attention-bound: 98.5 ms per 300 k rows), whole rings starve the TMA loop (112 ms); pairs: 94.4 ms.
+            if (g.burst > 1 && stage % g.burst == 0 && stage + g.burst <= STAGES && kb + g.burst <= num_kb) mbar_wait(&full[stage + g.burst - 1], phase);   // the burst's last k-block has landed
             mbar_wait(&full[stage], phase);
             if constexpr (DBG) w_ring += clock64() - c0;
             tc_fence_after();

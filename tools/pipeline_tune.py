@@ -1,5 +1,6 @@
-"""Chunk schedule of the strings -> results pipeline (`pipeline.score_strings_pipelined`) on the c2 workload:
-ms per 100 k strings for several (first_chunk_rows, chunk_rows). Usage: python tools/pipeline_tune.py"""
+"""Chunk schedule of the strings -> results pipeline (`pipeline.score_strings_pipelined`): ms per run for several
+(first_chunk_rows, chunk_rows) on the c2 workload (100 k strings, MiniLM) or, with `c3`, on the c3 workload (1 M strings,
+mpnet-base arch, 1000 names). Usage: python tools/pipeline_tune.py [c2|c3]"""
 import json
 import os
 import sys
@@ -17,24 +18,29 @@ from owc_b200.pipeline import score_strings_pipelined  # noqa: E402
 from owc_b200.tokenizer import HostTokenizer  # noqa: E402
 from owc_b200.weights import random_state_dict  # noqa: E402
 
-arch = A.MINILM_L6
-vocab = synth.build_vocab("bert", arch.vocab)
+wide = len(sys.argv) > 1 and sys.argv[1] == "c3"
+arch = A.MPNET_BASE if wide else A.MINILM_L6
+kind = "mpnet" if wide else "bert"
+vocab = synth.build_vocab(kind, arch.vocab)
 words = synth.vocab_words(vocab)
-tok = HostTokenizer(vocab, "bert")
+tok = HostTokenizer(vocab, kind)
 eng = Engine(arch, random_state_dict(arch), device=0)
-names = synth.real_class_names("food101")
-preds, targets = synth.make_predictions(100_000, names, words, seed=1)
+names = synth.make_class_names(1000, words, seed=1234) if wide else synth.real_class_names("food101")
+preds, targets = synth.make_predictions(1_000_000 if wide else 100_000, names, words, seed=1)
 ids, cu = tok.encode_packed(names)
 zc = eng.encode(ids, cu, out="device")
 res = {}
-for first, chunk in [(20000, 20000), (8000, 30000), (10000, 36000), (6000, 18000), (5000, 24000), (12000, 44000), (4000, 32000)]:
-    score_strings_pipelined(eng, tok, preds[:30000], zc, targets=targets[:30000], k=5, chunk_rows=chunk, first_chunk_rows=first)
-    best = 1e9
-    for _ in range(5):
+grid = ([(20000, 20000), (20000, 50000), (20000, 100000), (10000, 60000), (30000, 150000), (None, None)] if wide else
+        [(20000, 20000), (8000, 30000), (10000, 36000), (6000, 18000), (5000, 24000), (12000, 44000), (4000, 32000), (None, None)])
+for first, chunk in grid:
+    kw = {} if chunk is None else {"chunk_rows": chunk, "first_chunk_rows": first}   # (None, None): the library's default schedule
+    score_strings_pipelined(eng, tok, preds[:30000], zc, targets=targets[:30000], k=5, **kw)
+    times = []
+    for _ in range(3 if wide else 5):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        score_strings_pipelined(eng, tok, preds, zc, targets=targets, k=5, chunk_rows=chunk, first_chunk_rows=first)
-        best = min(best, (time.perf_counter() - t0) * 1e3)
-    res[f"{first}/{chunk}"] = round(best, 2)
+        score_strings_pipelined(eng, tok, preds, zc, targets=targets, k=5, **kw)
+        times.append(round((time.perf_counter() - t0) * 1e3, 1))
+    res[f"{first}/{chunk}"] = times
 print(json.dumps(res))
 eng.close()
