@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .pipeline import score_strings_pipelined
+from .pipeline import RowParts, score_jobs_pipelined
 
 __all__ = ["score_sweep"]
 
@@ -24,6 +24,8 @@ def score_sweep(engine, tokenizer, tasks: dict, k: int = 1, precision: str | Non
     Returns ``{task_name: {file_key: {"scores" [n,k], "idx" [n,k], "paired" [n] | None}}}`` (numpy, row order kept).
     """
     out: dict = {}
+    plan = []          # (task, keys, counts, with targets)
+    jobs = []          # (flat predictions, class embeddings on the device, targets)
     for task, spec in tasks.items():
         names = list(spec["class_names"])
         files = spec["files"]
@@ -32,16 +34,13 @@ def score_sweep(engine, tokenizer, tasks: dict, k: int = 1, precision: str | Non
             continue
         if k > len(names):
             raise ValueError(f"task {task!r}: k={k} exceeds its {len(names)} class names")
-        cids, ccu = tokenizer.encode_packed(names)
-        zc = engine.encode(cids, ccu, out="device", precision=precision)
         keys = list(files)
-        rows = [list(files[key]["predictions"]) for key in keys]
+        rows = [r if isinstance(r, list) else list(r) for r in (files[key]["predictions"] for key in keys)]
         have_t = [files[key].get("targets") is not None for key in keys]
         if any(have_t) and not all(have_t):
             raise ValueError(f"task {task!r}: either every file carries targets or none does")
         counts = [len(r) for r in rows]
-        flat = [p for r in rows for p in r]
-        if not flat:
+        if sum(counts) == 0:
             for key in keys:
                 out[task][key] = {"scores": np.zeros((0, k), np.float32), "idx": np.zeros((0, k), np.int32),
                                   "paired": np.zeros(0, np.float32) if all(have_t) else None}
@@ -49,13 +48,19 @@ def score_sweep(engine, tokenizer, tasks: dict, k: int = 1, precision: str | Non
         tg = None
         if all(have_t):
             tg = np.concatenate([np.asarray(files[key]["targets"], dtype=np.int32) for key in keys])
-            if tg.shape[0] != len(flat) or (tg.size and (tg.min() < 0 or tg.max() >= len(names))):
+            if tg.shape[0] != sum(counts) or (tg.size and (tg.min() < 0 or tg.max() >= len(names))):
                 raise ValueError(f"task {task!r}: targets do not match the predictions / class names")
-        # tokenisation of the next row chunk overlaps the device work of the previous one
-        res = score_strings_pipelined(engine, tokenizer, flat, zc, targets=tg, k=k, precision=precision)
+        cids, ccu = tokenizer.encode_packed(names)
+        zc = engine.encode(cids, ccu, out="device", precision=precision)   # each class set once (tiny; queued ahead of the rows)
+        plan.append((task, keys, counts, tg is not None))
+        jobs.append((RowParts(rows), zc, tg))    # concatenated by the pipeline's worker thread
+    # one pipeline over every task: the tokenisation of the next row chunk - of this task or the next one - overlaps the
+    # device work of the previous one, and the device is drained once, at the end
+    results = score_jobs_pipelined(engine, tokenizer, jobs, k=k, precision=precision)
+    for (task, keys, counts, with_t), res in zip(plan, results):
         lo = 0
         for key, c in zip(keys, counts):
             out[task][key] = {"scores": res["scores"][lo:lo + c], "idx": res["idx"][lo:lo + c],
-                              "paired": None if tg is None else res["paired"][lo:lo + c]}
+                              "paired": res["paired"][lo:lo + c] if with_t else None}
             lo += c
     return out
