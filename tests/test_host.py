@@ -353,3 +353,41 @@ def test_eval_metrics_parallel_io_is_byte_identical(oracle_backed, tmp_path):
         for model, out in serial[task].items():
             assert again[task][model].keys() == out.keys() and again[task][model]["_num_samples"] == out["_num_samples"]
             assert all(abs(again[task][model][k] - v) < 1e-9 for k, v in out.items())
+
+
+def test_jobs_pipeline_keeps_rows_in_order_across_jobs():
+    """pipeline.score_jobs_pipelined: chunks of several jobs run through one worker thread; every job gets its own rows
+    back in order (ragged chunking, an empty job, a job given as per-file row lists, targets on some jobs only)."""
+    from owc_b200.pipeline import RowParts, score_jobs_pipelined, score_strings_pipelined
+
+    class Tok:
+        def encode_packed(self, strings):
+            ids = np.asarray([int(s) for s in strings], np.int32)      # one "token" per row: the row's own number
+            return ids, np.arange(len(strings) + 1, dtype=np.int32)
+
+    class Eng:
+        def __init__(self):
+            self.calls = []
+
+        def score(self, ids, cu, zc, targets=None, k=1, precision=None, out="host"):
+            self.calls.append(len(ids))
+            s = np.repeat(ids[:, None].astype(np.float32), k, 1) + zc          # zc: the job's marker
+            return {"scores": s, "idx": np.repeat(ids[:, None], k, 1).astype(np.int32),
+                    "paired": None if targets is None else ids.astype(np.float32) * 2 + np.asarray(targets)}
+
+    a = [str(i) for i in range(53)]
+    b = RowParts([[str(i) for i in range(100, 117)], [], [str(i) for i in range(200, 230)]])
+    jobs = [(a, 1000.0, None), ([], 2000.0, None), (b, 3000.0, np.arange(47, dtype=np.int32))]
+    eng = Eng()
+    ra, re_, rb = score_jobs_pipelined(eng, Tok(), jobs, k=2, chunk_rows=20, first_chunk_rows=5)
+    assert eng.calls == [5, 20, 20, 8, 20, 20, 7]
+    assert np.array_equal(ra["idx"][:, 0], np.arange(53)) and np.array_equal(ra["scores"][:, 1], np.arange(53) + 1000.0) and ra["paired"] is None
+    assert re_["scores"].shape == (0, 2)
+    want_b = np.concatenate([np.arange(100, 117), np.arange(200, 230)])
+    assert np.array_equal(rb["idx"][:, 1], want_b) and np.array_equal(rb["paired"], want_b * 2.0 + np.arange(47))
+    one = score_strings_pipelined(Eng(), Tok(), a, 7.0, k=1, chunk_rows=16)
+    assert np.array_equal(one["scores"][:, 0], np.arange(53) + 7.0)
+    with pytest.raises(ValueError):
+        score_jobs_pipelined(Eng(), Tok(), [(a, 0.0, np.zeros(3, np.int32))])
+    with pytest.raises(NotImplementedError):
+        score_strings_pipelined(Eng(), Tok(), "not a list", 0.0)
