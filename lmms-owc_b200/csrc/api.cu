@@ -419,16 +419,18 @@ static int launch_gemm_wide(owc_ctx* c, const CUtensorMap& ta, const CUtensorMap
 }
 
 // QKV projection + attention of one layer on a chunk (qkv_attn.cuh). d_blk: the chunk's row-block table on the device.
-static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
+static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g, bool long_units) {
   owc_ctx* c = e->ctx;
-  OWC_TRY(ensure_smem_attr(c, k_qkv_attn<false>, qa::SMEM_BYTES));
-  if (c->wide_dbg) OWC_TRY(ensure_smem_attr(c, k_qkv_attn<true>, qa::SMEM_BYTES));
-  g.dbg = c->wide_dbg ? c->wide_dbg + 32 : nullptr;
-  g.burst = 2;   // measured: 1 -> 98.5, 2 -> 94.4, 4 -> 112 ms per 300 k rows (qkv_attn.cuh)
-  if (const char* bu = getenv("OWC_QKV_BURST")) g.burst = atoi(bu);
-  if (c->wide_dbg) {
+  const bool dbg = c->wide_dbg != nullptr;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const QkvAttnArgs) =
+      dbg ? (long_units ? k_qkv_attn<true, true> : k_qkv_attn<true, false>) : (long_units ? k_qkv_attn<false, true> : k_qkv_attn<false, false>);
+  OWC_TRY(ensure_smem_attr(c, kern, qa::SMEM_BYTES));
+  g.dbg = dbg ? c->wide_dbg + 32 : nullptr;
+  if (dbg) {
     if (const char* ex = getenv("OWC_WIDE_EXP")) g.exp = atoi(ex);   // instrumented build only (wrong results by construction)
   }
+  g.burst = -3;  // at most three k-blocks in the tensor pipe; same box, ms per 300 k rows: 0 (no limit) 90.6, pairs (2) 94.2, -2 85.1, -3 84.4
+  if (const char* bu = getenv("OWC_QKV_BURST")) g.burst = atoi(bu);
   const int n_items = (g.n_blk + 1) / 2;
   const int clusters = std::max(1, std::min(n_items, c->sm_count / 2));
   ProfScope prof(c, OWC_KCAT_GEMM, OWC_KCAT_GEMM_QKV);
@@ -442,8 +444,7 @@ static int launch_qkv_attn(owc_encoder* e, const LayerW& L, QkvAttnArgs g) {
   attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (c->wide_dbg) CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn<true>, e->tm_xb, L.tmh_wqkv, g));
-  else CU_OK(cudaLaunchKernelEx(&cfg, k_qkv_attn<false>, e->tm_xb, L.tmh_wqkv, g));
+  CU_OK(cudaLaunchKernelEx(&cfg, kern, e->tm_xb, L.tmh_wqkv, g));
   return check_launch(c, "k_qkv_attn");
 }
 
@@ -1139,7 +1140,7 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
       qa_args.inv_h = 1.0f / static_cast<float>(H); qa_args.ln_eps = a.ln_eps;
       qa_args.ao = e->ao; qa_args.ldo = H;
       qa_args.scale_log2 = aa.scale * 1.4426950408889634f; qa_args.rel_lut = e->rel_lut; qa_args.max_pos = a.max_pos;
-      OWC_TRY(launch_qkv_attn(e, L, qa_args));
+      OWC_TRY(launch_qkv_attn(e, L, qa_args, max_t > 16));
     } else {
       OWC_TRY(launch_gemm_wide<WEPI_FOLD_BF16>(c, e->tm_xb, L.tmf_wqkv, e->tmo_qkv, e->tmo_qkv, g, OWC_KCAT_GEMM_QKV));
       if (aa.grp != nullptr) OWC_TRY(launch_attn_grp(e, aa));

@@ -9,11 +9,15 @@
 //     are simply the next block's rows, computed and ignored (nothing is ever stored for them);
 //   * column tiles of 192 = one head's [q | k | v] (the gamma-folded weight rows are regrouped per head at load time), so an
 //     accumulator holds everything one head needs for the block;
-//   * an epilogue that applies the deferred LayerNorm (out = rstd_r (acc - mu_r c1[n]) + c2[n]), writes the head's bf16
-//     q|k|v rows into shared memory (XOR-swizzled 16-byte chunks: every fragment access below is bank-conflict free), runs
-//     the attention of the block's sequences on the warp-level tensor path (several short sequences per 16 x 16 tile, as in
-//     k_attn_grp) and writes ONLY the attention output rows to global memory (the A operand of the O-projection).
-// The MMAs of head h+1 run while the epilogue warps work on head h (two TMEM accumulators of 192 columns).
+//   * an epilogue split over two warp roles. DRAIN warps (one TMEM lane quadrant each) apply the deferred LayerNorm
+//     (out = rstd_r (acc - mu_r c1[n]) + c2[n]) and write the head's bf16 q|k|v rows into shared memory (XOR-swizzled 16-byte
+//     chunks: every fragment access below is bank-conflict free). ATTENTION warps take one unit each - several short sequences
+//     per 16 x 16 tile, as in k_attn_grp - pull the unit's fragments into registers with twelve ldmatrix.x4, give the rows back
+//     to the drain warps at once, run the attention on the warp-level tensor path and store ONLY the attention output rows to
+//     global memory (the A operand of the O-projection), straight from the fragments.
+// The MMAs of head h+2, the drain of head h+1 and the attention of head h overlap (two TMEM accumulators of 192 columns, one
+// q|k|v buffer, a 6-stage TMA ring). The warp-level MMAs share the tensor core with the tcgen05 stream and queue behind the
+// UMMAs in flight, so the MMA warp keeps at most three k-blocks in the tensor pipe (see DESIGN.md 3c for the measurements).
 // Reference semantics: modeling_mpnet.py:116-186 / modeling_bert.py:114-207 (scaled dot-product attention with the
 // additive relative-position bias of MPNet; packed sequences carry no padding, so the padding mask is a no-op).
 #pragma once
@@ -44,7 +48,7 @@ struct QkvAttnArgs {
   const float* rel_lut;      // MPNet: [heads, 2 * max_pos - 1] bias by (k - q), or nullptr
   int max_pos;
   long long* dbg;            // instrumented build: cycle counters (see k_qkv_attn), else unused
-  int burst;                 // > 1: the MMA warp issues this many k-blocks back to back once the last of them has landed (env OWC_QKV_BURST)
+  int burst;                 // < 0: at most -burst k-blocks in the tensor pipe (default -3); > 1: bursts of that many; 0 / 1: no limit (env OWC_QKV_BURST)
   int exp;                   // instrumented build only, WRONG results: bit 1 = skip the attention of every unit (MMA + drain alone), bit 2 = issue no UMMA (TMA + drain + attention alone)
 };
 
@@ -55,7 +59,7 @@ constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int BH_BYTES = (BN / 2) * BK * 2; // 12 KB: this CTA's 96 rows of the head's weight tile
 constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 // Warp roles. The drain warps own one TMEM lane quadrant each (warp id % 4 selects the quadrant a warp may read); the
 // attention warps follow; the two single-lane issue roles take the TOP ids: the warp scheduler favours the highest warp id
 // of an SMSP and the other warps are busy, so on ids 0 / 1 the TMA / MMA issue loops starve (measured: 14.5 k clk per head
@@ -65,18 +69,22 @@ constexpr int ATT_WARPS = 10;                // 16 warps = 4 per scheduler: 128 
 constexpr int DRAIN_THREADS = DRAIN_WARPS * 32, ATT_THREADS = ATT_WARPS * 32;
 constexpr int W_TMA = DRAIN_WARPS + ATT_WARPS, W_MMA = W_TMA + 1;
 constexpr int THREADS = (W_MMA + 1) * 32;
-constexpr int MAX_HEADS = 12;               // the relative-position bias slices of every head live in shared memory
 constexpr int QROW = 3 * D * 2;             // 384 B per q|k|v row
-constexpr int QKV_BYTES = BM * QROW;        // 48 KB, twice: the rows of head h + 1 are written while head h is attended
+// ONE 48 KB q|k|v buffer: an attention warp holds its whole unit in registers after twelve ldmatrix.x4 and gives the rows back
+// before it computes, so the drain of head h + 1 runs under the attention of head h without a second buffer - and the ring
+// gets the shared memory (6 stages instead of 4: the TMA -> UMMA loop was latency-bound, the MMA warp waited 50-57 % of its
+// time for operands).
+constexpr int QKV_BYTES = BM * QROW;
 constexpr int OFF_QKV = STAGES * STAGE_BYTES;
-constexpr int OFF_TAIL = OFF_QKV + 2 * QKV_BYTES;
+constexpr int OFF_TAIL = OFF_QKV + QKV_BYTES;
 constexpr int TBL_BYTES = 544 /*seq_row*/ + 144 /*grp_first*/ + 16 /*n_grp*/ + 256 /*row_rng*/;   // per item parity
 constexpr int OFF_TBL = 256 /*barriers, tmem slot*/;
 constexpr int OFF_PARAM = OFF_TBL + 2 * TBL_BYTES;               // c1 | c2 of one head, two parities: 3 KB
-constexpr int OFF_LUT = OFF_PARAM + 2 * 2 * BN * 4;              // bias slices: 6 KB
-constexpr int TAIL_BYTES = OFF_LUT + MAX_HEADS * 128 * 4;
+constexpr int MAX_HEADS = 16;
+constexpr int OFF_LUT = OFF_PARAM + 2 * 2 * BN * 4;              // bias of (key - query) in -15 .. 15 for every head (log2 domain): 2 KB
+constexpr int TAIL_BYTES = OFF_LUT + MAX_HEADS * 32 * 4;
 // With 200+ KB of shared memory the L1 keeps nothing: every __ldg in the epilogue is an L2 round trip (~800 clk), so what a
-// head tile needs is staged ahead of time (bias slices once per kernel, c1 | c2 one head ahead).
+// head tile needs is staged ahead of time (c1 | c2 one head ahead; the bias values a 16 x 16 score tile can need once per kernel).
 constexpr int SMEM_BYTES = 1024 + OFF_TAIL + TAIL_BYTES;
 static_assert(SMEM_BYTES <= kSmemLimit, "shared memory budget");
 }  // namespace qa
@@ -90,8 +98,11 @@ __device__ __forceinline__ uint8_t* qa_chunk(uint8_t* qkv, int row, int c) {
 // One attention unit out of the shared q|k|v rows: a GROUP of consecutive sequences (<= 16 rows together, block-diagonal
 // mask; TP == 16) or one longer sequence (TP == 32 / 64). Rows [beg, beg + T) of the block. The output overwrites the unit's
 // own (dead) q chunks and is then copied out with 16-byte row-contiguous stores.
+// Not inlined: these 32- / 64-row tiles are the rare path (sequences longer than 16 tokens) and need more registers than the
+// 128 a thread of this kernel has; inlined, their pressure spilled the HOT loop's counters to local memory - which, with the
+// L1 squeezed to nothing by 227 KB of shared memory, is an L2 round trip per access (9 % of the kernel's stall samples).
 template <int TP, bool DBG = false>
-__device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const int* seq_row, int s_first, int s_last, int lane,
+__device__ __noinline__ void qa_attend(uint8_t* qkv, int beg, int T, const int* seq_row, int s_first, int s_last, int lane,
                                           float scale_log2, const float* lut, __nv_bfloat16* out, int ldo, long long* ph = nullptr) {
   constexpr int NT = TP / 8, MT = TP / 16, DN = qa::D / 8;
   const int g = lane >> 2, t4 = lane & 3;
@@ -153,7 +164,7 @@ __device__ __forceinline__ void qa_attend(uint8_t* qkv, int beg, int T, const in
           const int i = (e < 2) ? r0 : r1;
           const bool ok = (e < 2) ? (j >= lo0 && j < hi0) : (j >= lo1 && j < hi1);
           float v = s[nt][e] * scale_log2;
-          if (lut != nullptr && ok) v += lut[j - i];   // shared memory, already in the log2 domain
+          if (lut != nullptr && ok) v += __ldg(lut + (j - i)) * 1.4426950408889634f;   // global (L2): the rare long-sequence path
           v = ok ? v : -INFINITY;
           s[nt][e] = v;
           if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
@@ -253,9 +264,11 @@ __device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (
 // the k-steps of Q K^T accumulate into separate registers that are summed afterwards - and the unit waits on the tensor core
 // twice (scores, P V) instead of five times; all fragments come in by ldmatrix.x4 before the first MMA.
 // row_rng[r] = first | (end << 8) of the block-relative key range of row r's sequence.
+// lut: the head's relative-position bias by (key - query), log2 domain, in shared memory (or null). release: if not null, the unit is the warp's last of this head: once the fragments are in registers
+// the warp arrives there and the drain warps may overwrite the rows.
 template <bool DBG>
 __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const uint16_t* row_rng, int lane, float scale_log2,
-                                            const float* lut, __nv_bfloat16* out, int ldo, long long* ph) {
+                                            const float* lut, __nv_bfloat16* out, int ldo, long long* ph, uint64_t* release) {
   const int g = lane >> 2, t4 = lane & 3;
   long long pc = 0;
   if constexpr (DBG) pc = clock64();
@@ -280,18 +293,36 @@ __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const 
   int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
   if (r0 < T) { const int v = row_rng[beg + r0]; lo0 = (v & 0xff) - beg; hi0 = (v >> 8) - beg; }
   if (r1 < T) { const int v = row_rng[beg + r1]; lo1 = (v & 0xff) - beg; hi1 = (v >> 8) - beg; }
-  stamp(0);
-  float sp[4][2][4];
+  if (release != nullptr) {
+    // one register of each ldmatrix feeds a real instruction, so the scoreboard holds the arrive back until all twelve loads
+    // have delivered (the arrive itself does not read them)
+    uint32_t x = 0;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+    for (int i = 0; i < 4; ++i) x ^= qf[i][3] ^ kf[i][3] ^ vf[i][3];
+    asm volatile("" ::"r"(x) : "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release);
+  }
+  stamp(0);
+  // two chains of two k-steps per n-tile: four independent accumulators per n-tile cost 16 more registers than the thread has
+  // to spare (the loop state went to local memory = L2 round trips), one dependent step costs ~100 clk
+  float sp[2][2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
     mma_bf16_16816_z(sp[ks][0], qf[ks], kf[ks][0], kf[ks][1]);
     mma_bf16_16816_z(sp[ks][1], qf[ks], kf[ks][2], kf[ks][3]);
+  }
+#pragma unroll
+  for (int ks = 2; ks < 4; ++ks) {
+    const uint32_t b0[2] = {kf[ks][0], kf[ks][1]}, b1[2] = {kf[ks][2], kf[ks][3]};
+    mma_bf16_16816(sp[ks - 2][0], qf[ks], b0);
+    mma_bf16_16816(sp[ks - 2][1], qf[ks], b1);
   }
   float s[2][4];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) s[nt][e] = (sp[0][nt][e] + sp[1][nt][e]) + (sp[2][nt][e] + sp[3][nt][e]);
+    for (int e = 0; e < 4; ++e) s[nt][e] = sp[0][nt][e] + sp[1][nt][e];
   stamp(1);
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
@@ -302,7 +333,7 @@ __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const 
       const int i = (e < 2) ? r0 : r1;
       const bool ok = (e < 2) ? (j >= lo0 && j < hi0) : (j >= lo1 && j < hi1);
       float v = s[nt][e] * scale_log2;
-      if (lut != nullptr && ok) v += lut[j - i];   // shared memory, already in the log2 domain
+      if (lut != nullptr && ok) v += lut[j - i];
       v = ok ? v : -INFINITY;
       s[nt][e] = v;
       if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
@@ -359,12 +390,21 @@ __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const 
 }
 
 
+// Out-of-line copy for blocks that also hold longer sequences (their head loop makes calls, see qa_attend).
+template <bool DBG>
+__device__ __noinline__ void qa_attend16_call(uint8_t* qkv, int beg, int T, const uint16_t* row_rng, int lane, float scale_log2,
+                                              const float* lut, __nv_bfloat16* out, int ldo, long long* ph) {
+  qa_attend16<DBG>(qkv, beg, T, row_rng, lane, scale_log2, lut, out, ldo, ph, nullptr);
+}
+
 // Cycle counters of the instrumented build (g.dbg, leader CTAs only, accumulated with atomics):
 //   [0] MMA warp: ring wait  [1] accumulator wait  [2] MMA warp total  [3] drain warp 0: accumulator (tfull) wait
 //   [4] drain warp 0: q|k|v buffer wait  [5] drain warp 0 total  [6] CTAs  [8] attention warp 0: q|k|v rows wait
 //   [9] attention warp 0: table building  [10] attention warp 0 total  [11..15] its phases of qa_attend: tile bounds, QK,
 //   softmax, PV, rows to shared memory (the write-back is the rest)  [7] attention units of warp 0
-template <bool DBG>
+// LONG = false: every sequence of the chunk has at most 16 tokens (labels: the benchmark's all do), so the attention warps'
+// loop holds the inlined 16 x 16 tile only - no call whose ABI would push the loop's live values to local memory.
+template <bool DBG, bool LONG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(qa::THREADS, 1)
 k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QkvAttnArgs g) {
   using namespace qa;
@@ -380,7 +420,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint64_t* qfree = qfull + 2;            // ... and read for the last time (attention warps -> drain warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfree + 2);
   float* param_s = reinterpret_cast<float*>(tail + OFF_PARAM);         // [2][c1 | c2][BN]
-  float* lut_s = reinterpret_cast<float*>(tail + OFF_LUT);             // [heads][128]: bias of offset d at [h][d + 63], log2 domain
+  float* lut_s = reinterpret_cast<float*>(tail + OFF_LUT);             // [heads][32]: bias of offset d at [h][d + 15], log2 domain
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -398,7 +438,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 2 * DRAIN_WARPS);
-      mbar_init(&qfull[b], DRAIN_WARPS);
+      mbar_init(&qfull[b], DRAIN_WARPS);     // only [0] is used: one q|k|v buffer
       mbar_init(&qfree[b], ATT_WARPS);
     }
     fence_barrier_init();
@@ -457,10 +497,10 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
             if constexpr (DBG) c0 = clock64();
-            // Pairs of k-blocks go to the tensor pipe back to back, with a gap before the next pair: the warp-level MMAs of the
-            // attention queue behind UMMAs in flight (see qa_attend16) and get through in the gaps. One k-block at a time
-            // leaves no gap (attention-bound: 98.5 ms per 300 k rows), whole rings starve the TMA loop (112 ms); pairs: 94.4 ms.
-            if (g.burst > 1 && stage % g.burst == 0 && stage + g.burst <= STAGES && kb + g.burst <= num_kb) mbar_wait(&full[stage + g.burst - 1], phase);   // the burst's last k-block has landed
+            // A/B switch: burst > 1 = wait until that many k-blocks have landed, then issue them back to back (the gaps between
+            // bursts let the attention's HMMAs through, but waiting for data that is not needed yet costs the TMA-bound stream
+            // 28 %; kept for measurements).
+            if (g.burst > 1 && stage % g.burst == 0 && stage + g.burst <= STAGES && kb + g.burst <= num_kb) mbar_wait(&full[stage + g.burst - 1], phase);
             mbar_wait(&full[stage], phase);
             if constexpr (DBG) w_ring += clock64() - c0;
             tc_fence_after();
@@ -470,6 +510,17 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               umma_commit_2sm(&empty[stage]);
             }
             __syncwarp();
+            if (g.burst < 0) {
+              // The default (burst = -3): at most three k-blocks in the tensor pipe. mma.sync shares the tensor core with the
+              // tcgen05 stream and queues behind the UMMAs in flight (see qa_attend16); with the MMA warp running a whole ring
+              // ahead the attention units wait ~0.5 k clk per HMMA phase. So the warp waits for the commit of the k-block it
+              // issued two steps ago (the barrier that also gives that slot back to the TMA warp) before it issues the next:
+              // the queue stays short, the stream - TMA-bound anyway - loses nothing. Same box, 300 k rows: no limit 90.6 ms,
+              // <= 1 in flight 113 ms (the pipe idles between k-blocks), <= 2: 85.1 ms, <= 3: 84.4 ms.
+              const int back = -g.burst - 1;
+              const int ps = stage >= back ? stage - back : stage - back + STAGES;
+              mbar_wait(&empty[ps], stage >= back ? phase : phase ^ 1u);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (elect_one_sync()) umma_commit_2sm(&tfull[buf]);
@@ -533,12 +584,12 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         float pn[3];
         ld_params(h + 1 < g.heads ? h + 1 : 0, pn);
         if constexpr (DBG) c0 = clock64();
-        mbar_wait(&qfree[buf], par ^ 1u);       // the attention of head t - 2 has left this q|k|v buffer
+        mbar_wait(&qfree[0], (t & 1u) ^ 1u);    // every attention warp holds its last unit of head t - 1 in registers
         if constexpr (DBG) { const long long c1 = clock64(); w_qfree += c1 - c0; c0 = c1; }
         mbar_wait(&tfull[buf], par);
         if constexpr (DBG) w_tfull += clock64() - c0;
         tc_fence_after();
-        uint8_t* qb = qkv_s + buf * QKV_BYTES;
+        uint8_t* qb = qkv_s;
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * BN;
         // six 32-column chunks of the head tile (q: 0,1  k: 2,3  v: 4,5), the next one in flight while one is converted
         uint32_t v[2][32];
@@ -573,7 +624,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));   // accumulator drained: the MMAs of head t + 2 may start
-          mbar_arrive(&qfull[buf]);                                   // this warp's 32 rows of the head are in shared memory
+          mbar_arrive(&qfull[0]);                                     // this warp's 32 rows of the head are in shared memory
         }
         named_bar_sync(3, DRAIN_THREADS);       // the next head's parameters are staged
       }
@@ -589,9 +640,9 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // ---------------- attention warps: the block's sequences, head by head, out of the shared q|k|v rows ----------------
     const int aw = warp - DRAIN_WARPS;
     const int at = threadIdx.x - DRAIN_THREADS;
-    for (int i = at; i < g.heads * 128; i += ATT_THREADS) {
-      const int h = i >> 7, d = (i & 127) - 63;
-      lut_s[i] = (g.rel_lut != nullptr && d <= 63) ? __ldg(g.rel_lut + static_cast<size_t>(h) * (2 * g.max_pos - 1) + g.max_pos - 1 + d) * 1.4426950408889634f : 0.f;
+    for (int i = at; i < g.heads * 32; i += ATT_THREADS) {   // visible after the first item's table barrier
+      const int h = i >> 5, d = (i & 31) - 15;
+      lut_s[i] = (g.rel_lut != nullptr && d <= 15) ? __ldg(g.rel_lut + static_cast<size_t>(h) * (2 * g.max_pos - 1) + g.max_pos - 1 + d) * 1.4426950408889634f : 0.f;
     }
     uint32_t t = 0;
     uint32_t ip = 0;                            // item parity: the tables of item i + 1 are built while stragglers read item i's
@@ -613,7 +664,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       for (int i = at; i <= nseq; i += ATT_THREADS) seq_row[i] = __ldg(g.cu + s0 + i) - g.tok0 - row0;
       named_bar_sync(1, ATT_THREADS);
       if (at == 0) {
-        int ng = 0, rows = 0;
+        int ng = 0, rows = 0, longest = 0;
         grp_first[0] = 0;
         for (int i = 0; i < nseq; ++i) {
           const int len = seq_row[i + 1] - seq_row[i];
@@ -622,9 +673,11 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             rows = 0;
           }
           rows += len;
+          longest = max(longest, len);
         }
         if (nseq > 0) grp_first[++ng] = static_cast<uint8_t>(nseq);
-        *n_grp_s = ng;
+        n_grp_s[0] = ng;
+        n_grp_s[1] = longest > 16;              // the block holds a unit for the 32- / 64-row tiles
       }
       for (int i = ATT_THREADS - 1 - at; i < nseq; i += ATT_THREADS) {   // thread 0 is busy with the groups
         const int b = seq_row[i], e = seq_row[i + 1];
@@ -632,27 +685,46 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
       named_bar_sync(1, ATT_THREADS);
       if constexpr (DBG) w_tbl += clock64() - c0;
-      const int n_grp = *n_grp_s;
+      const int n_grp = n_grp_s[0];
+      const bool has_long = n_grp_s[1] != 0;
       for (int h = 0; h < g.heads; ++h, ++t) {
-        const uint32_t buf = t & 1u;
+        const float* lut_g = g.rel_lut ? g.rel_lut + static_cast<size_t>(h) * (2 * g.max_pos - 1) + g.max_pos - 1 : nullptr;
+        const float* lut16 = g.rel_lut ? lut_s + h * 32 + 15 : nullptr;
         if constexpr (DBG) c0 = clock64();
-        mbar_wait(&qfull[buf], (t >> 1) & 1u);
+        mbar_wait(&qfull[0], t & 1u);
         if constexpr (DBG) w_qfull += clock64() - c0;
-        uint8_t* qb = qkv_s + buf * QKV_BYTES;
-        const float* lut = g.rel_lut ? lut_s + h * 128 + 63 : nullptr;
         __nv_bfloat16* out = g.ao + static_cast<size_t>(row0) * g.ldo + h * D;
-        for (int u = aw; u < n_grp; u += ATT_WARPS) {
-          const int s_first = grp_first[u], s_last = grp_first[u + 1];
-          const int beg = seq_row[s_first];
-          const int T = seq_row[s_last] - beg;
-          if (T <= 0) continue;
-          if (DBG && (g.exp & 2)) continue;
-          if (T <= 16) qa_attend16<DBG>(qb, beg, T, row_rng, lane, g.scale_log2, lut, out, g.ldo, ph);
-          else if (T <= 32) qa_attend<32, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
-          else qa_attend<64, DBG>(qb, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut, out, g.ldo, ph);
+        if (!LONG || !has_long) {
+          // the hot loop: 16 x 16 tiles only, everything inlined, no call in sight of its live registers
+          bool released = false;
+          for (int u = aw; u < n_grp; u += ATT_WARPS) {
+            const int s_first = grp_first[u], s_last = grp_first[u + 1];
+            const int beg = seq_row[s_first];
+            const int T = seq_row[s_last] - beg;
+            if (T <= 0) continue;
+            if (DBG && (g.exp & 2)) continue;
+            const bool last = u + ATT_WARPS >= n_grp;
+            qa_attend16<DBG>(qkv_s, beg, T, row_rng, lane, g.scale_log2, lut16, out, g.ldo, ph, last ? &qfree[0] : nullptr);
+            released = released || last;
+          }
+          if (!released) {   // no unit for this warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qfree[0]);
+          }
+        } else if constexpr (LONG) {
+          // a block with longer sequences: out-of-line tiles that read the rows while they compute; the rows go back afterwards
+          for (int u = aw; u < n_grp; u += ATT_WARPS) {
+            const int s_first = grp_first[u], s_last = grp_first[u + 1];
+            const int beg = seq_row[s_first];
+            const int T = seq_row[s_last] - beg;
+            if (T <= 0) continue;
+            if (T <= 16) qa_attend16_call<DBG>(qkv_s, beg, T, row_rng, lane, g.scale_log2, lut16, out, g.ldo, ph);
+            else if (T <= 32) qa_attend<32, DBG>(qkv_s, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut_g, out, g.ldo, ph);
+            else qa_attend<64, DBG>(qkv_s, beg, T, seq_row, s_first, s_last, lane, g.scale_log2, lut_g, out, g.ldo, ph);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&qfree[0]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&qfree[buf]);
       }
     }
     if constexpr (DBG) {
