@@ -48,6 +48,7 @@ struct QkvAttnArgs {
   const float* rel_lut;      // MPNet: [heads, 2 * max_pos - 1] bias by (k - q), or nullptr
   int max_pos;
   long long* dbg;            // instrumented build: cycle counters (see k_qkv_attn), else unused
+  uint32_t zero;             // always 0 (an operand the compilers cannot fold: see qa_attend16)
   int burst;                 // < 0: at most -burst k-blocks in the tensor pipe (default -3); > 1: bursts of that many; 0 / 1: no limit (env OWC_QKV_BURST)
   int exp;                   // instrumented build only, WRONG results: bit 1 = skip the attention of every unit (MMA + drain alone), bit 2 = issue no UMMA (TMA + drain + attention alone)
 };
@@ -268,7 +269,8 @@ __device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (
 // the warp arrives there and the drain warps may overwrite the rows.
 template <bool DBG>
 __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const uint16_t* row_rng, int lane, float scale_log2,
-                                            const float* lut, __nv_bfloat16* out, int ldo, long long* ph, uint64_t* release) {
+                                            const float* lut, __nv_bfloat16* out, int ldo, long long* ph, uint64_t* release,
+                                            uint32_t zero = 0) {
   const int g = lane >> 2, t4 = lane & 3;
   long long pc = 0;
   if constexpr (DBG) pc = clock64();
@@ -294,14 +296,16 @@ __device__ __forceinline__ void qa_attend16(uint8_t* qkv, int beg, int T, const 
   if (r0 < T) { const int v = row_rng[beg + r0]; lo0 = (v & 0xff) - beg; hi0 = (v >> 8) - beg; }
   if (r1 < T) { const int v = row_rng[beg + r1]; lo1 = (v & 0xff) - beg; hi1 = (v >> 8) - beg; }
   if (release != nullptr) {
-    // one register of each ldmatrix feeds a real instruction, so the scoreboard holds the arrive back until all twelve loads
-    // have delivered (the arrive itself does not read them)
+    // The arrive is a release: the loads above are ordered before it. On top of that, one register of each ldmatrix feeds the
+    // barrier's ADDRESS (and-ed with a kernel argument that is zero, so neither compiler can fold it away): the scoreboard
+    // holds the arrive back until all twelve loads have delivered.
     uint32_t x = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) x ^= qf[i][3] ^ kf[i][3] ^ vf[i][3];
-    asm volatile("" ::"r"(x) : "memory");
     __syncwarp();
-    if (lane == 0) mbar_arrive(release);
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(release) + (x & zero)) : "memory");
+    }
   }
   stamp(0);
   // two chains of two k-steps per n-tile: four independent accumulators per n-tile cost 16 more registers than the thread has
@@ -704,7 +708,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (T <= 0) continue;
             if (DBG && (g.exp & 2)) continue;
             const bool last = u + ATT_WARPS >= n_grp;
-            qa_attend16<DBG>(qkv_s, beg, T, row_rng, lane, g.scale_log2, lut16, out, g.ldo, ph, last ? &qfree[0] : nullptr);
+            qa_attend16<DBG>(qkv_s, beg, T, row_rng, lane, g.scale_log2, lut16, out, g.ldo, ph, last ? &qfree[0] : nullptr, g.zero);
             released = released || last;
           }
           if (!released) {   // no unit for this warp
