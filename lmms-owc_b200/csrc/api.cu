@@ -1291,11 +1291,28 @@ static int encode_all(owc_encoder* e, const int32_t* ids, int ids_space, const i
   OWC_TRY(to_device(c, c->cu, cu, (static_cast<size_t>(n_seq) + 1) * sizeof(int32_t), OWC_MEM_HOST, &d_cu));
   if (precision == OWC_PREC_BF16 && c->fused && e->fused_ok && longest <= 64)
     return encode_all_fused(e, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_cu), cu, n_seq, z, zb);
+  // k_qkv_attn works on row blocks of whole sequences (<= 128 rows, packed greedily: ~126 on labels), two per cluster and
+  // item. A chunk cut by tokens alone holds ~1.6 % more blocks than whole waves of clusters (602 items over 74 clusters: a
+  // ninth, nearly empty wave = 10 % of that kernel's time), so on that path a chunk also ends after `wide_waves` waves of blocks.
+  const bool by_blocks = e->wide_ln && precision == OWC_PREC_BF16 && e->qkv_attn && c->qkv_attn && longest <= 64;
+  const int blk_cap = by_blocks ? (c->sm_count / 2) * 2 * c->wide_waves : 0;
   int s0 = 0;
   while (s0 < n_seq) {
     int s1 = s0, max_t = 1;
+    int blocks = 1, rows = 0, cnt = 0;     // the packing rule of encode_chunk_wide
     while (s1 < n_seq && cu[s1 + 1] - cu[s0] <= e->cap) {
-      max_t = std::max(max_t, cu[s1 + 1] - cu[s1]);
+      const int len = cu[s1 + 1] - cu[s1];
+      if (by_blocks) {
+        if (rows + len > 128 || cnt == 128) {
+          if (blocks == blk_cap) break;
+          ++blocks;
+          rows = 0;
+          cnt = 0;
+        }
+        rows += len;
+        ++cnt;
+      }
+      max_t = std::max(max_t, len);
       ++s1;
     }
     if (s1 == s0) return fail("internal: chunk capacity %d below one sequence", e->cap);
