@@ -129,10 +129,12 @@ struct owc_encoder {
   int cap = 0;                     // workspace rows (tokens per chunk)
   float *x = nullptr, *y = nullptr;
   __nv_bfloat16 *xb = nullptr, *qkv = nullptr, *ao = nullptr, *f = nullptr;
+  __nv_bfloat16* xl = nullptr;               // wide path: low half of the residual stream's bf16 pair (xb is the high half)
   float *qkv32 = nullptr, *ao32 = nullptr, *f32 = nullptr;   // check mode, allocated on first use
   CUtensorMap tm_xb, tm_ao, tm_f;            // A-operand maps (box 128 rows x 64)
   CUtensorMap tmo_qkv, tmo_f, tmo_y;         // epilogue TMA-store maps (box 32 x 32)
   CUtensorMap tmo_x, tmo_xb;                 // fused-LN epilogue: residual stream (fp32, load + store) and its bf16 copy
+  CUtensorMap tmo_xl;                        // wide path: xl (load + store, as tmo_xb)
   // block-resident fused encoder (enc_fused.cuh): layer-stacked bf16 weights, QKV rows regrouped per head
   bool fused_ok = false;
   __nv_bfloat16 *fw_qkv = nullptr, *fw_o = nullptr, *fw_1 = nullptr, *fw_2 = nullptr;
@@ -641,7 +643,7 @@ extern "C" int32_t owc_encoder_destroy(owc_encoder* e) {
   if (!e) return 0;
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
-  void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32,
+  void* ptrs[] = {e->w32, e->w16, e->x, e->y, e->xb, e->xl, e->qkv, e->ao, e->f, e->qkv32, e->ao32, e->f32,
                   e->fw_qkv, e->fw_o, e->fw_1, e->fw_2, e->fx, e->fdbg, e->wfold16, e->wfold32, e->st1, e->st2, e->wfold16h, e->wfold32h};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -745,6 +747,9 @@ extern "C" int32_t owc_encoder_load(owc_ctx* c, const owc_arch* arch, const floa
   // ---- deferred-LayerNorm path of wide encoders (gemm_wide.cuh): gamma-folded Wqkv / W1 and their epilogue vectors ----
   if (e->wide_ln) {
     const size_t L = a.layers;
+    LOAD_CU(cudaMalloc(&e->xl, cap * h * sizeof(__nv_bfloat16)));
+    LOAD_CU(cudaMemsetAsync(e->xl, 0, cap * h * sizeof(__nv_bfloat16), c->stream));
+    if (make_out_tmap(c, &e->tmo_xl, e->xl, cap, h, true)) { owc_encoder_destroy(e); return 1; }
     LOAD_CU(cudaMalloc(&e->wfold16, L * (3 * h * h + I * h) * sizeof(__nv_bfloat16)));
     LOAD_CU(cudaMalloc(&e->wfold32, L * 2 * (3 * h + I) * sizeof(float)));
     const size_t stat_bytes = kWideStatSlots * cap * 2 * sizeof(float);
@@ -1051,7 +1056,8 @@ static int encode_chunk(owc_encoder* e, const int32_t* d_ids, const int32_t* d_c
 
 // Wide encoders (H = 768) in bf16: persistent CTA-pair GEMMs with the LayerNorms deferred into their consumers
 // (gemm_wide.cuh). Per layer: QKV (fold) -> attention -> O-projection (+residual, statistics) -> FFN1 (fold + GELU)
-// -> FFN2 (+residual, statistics); e->x holds the PRE-LayerNorm sum y, e->xb its bf16 copy, st1 / st2 the row statistics.
+// -> FFN2 (+residual, statistics); the PRE-LayerNorm sum y lives as the bf16 pair e->xb (high half = the GEMMs' A operand) +
+// e->xl (low half), st1 / st2 are the row statistics.
 static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* cu, int seq0, int n_seq,
                              int tok0, int M, int max_t, float* z, __nv_bfloat16* zb) {
   owc_ctx* c = e->ctx;
@@ -1063,7 +1069,7 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
   ea.word = e->word; ea.pos = e->pos; ea.type0 = e->type0; ea.gamma = e->emb_g; ea.beta = e->emb_b;
   ea.eps = a.ln_eps; ea.H = H; ea.vocab = a.vocab; ea.max_pos = a.max_pos;
   ea.mpnet = a.kind == OWC_ARCH_MPNET; ea.pad_id = a.pad_id;
-  ea.x = e->x; ea.xb = e->xb; ea.status = c->d_status; ea.stats = e->st2;
+  ea.x = nullptr; ea.xb = e->xb; ea.xl = e->xl; ea.status = c->d_status; ea.stats = e->st2;
   {
     ProfScope prof(c, OWC_KCAT_EMBED);
     DISPATCH_NV(H, k_embed_ln<NV, true><<<embed_grid(c, n_seq), 128, 0, c->stream>>>(ea));
@@ -1149,22 +1155,22 @@ static int encode_chunk_wide(owc_encoder* e, const int32_t* d_ids, const int32_t
     }
     g = WideArgs{};
     g.M = M; g.N = H; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
-    g.bias = L.bo; g.y = e->x; g.stats_prev = e->st2; g.slots_in = slots2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;
-    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_O));
+    g.bias = L.bo; g.stats_prev = e->st2; g.slots_in = slots2; g.gamma_prev = g_in; g.beta_prev = b_in; g.stats_out = e->st1;
+    OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_ao, L.tmw_wo, e->tmo_xl, e->tmo_xb, g, OWC_KCAT_GEMM_O));
     g = WideArgs{};
     g.M = M; g.N = I; g.K = H; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
     g.c1 = L.c1f; g.c2 = L.c2f; g.stats_in = e->st1; g.slots_in = o_slots;
     OWC_TRY(launch_gemm_wide<WEPI_FOLD_GELU_BF16>(c, e->tm_xb, L.tmf_w1, e->tmo_f, e->tmo_f, g, OWC_KCAT_GEMM_FFN1));
     g = WideArgs{};
     g.M = M; g.N = H; g.K = I; g.inv_h = 1.0f / static_cast<float>(H); g.ln_eps = a.ln_eps; g.stat_stride = stride;
-    g.bias = L.b2; g.y = e->x; g.stats_prev = e->st1; g.slots_in = o_slots; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
-    if (c->wide_deep) OWC_TRY(launch_gemm_wide<WEPI_RES_STATS_DEEP>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
-    else OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_x, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
+    g.bias = L.b2; g.stats_prev = e->st1; g.slots_in = o_slots; g.gamma_prev = L.ln1g; g.beta_prev = L.ln1b; g.stats_out = e->st2;
+    if (c->wide_deep) OWC_TRY(launch_gemm_wide<WEPI_RES_STATS_DEEP>(c, e->tm_f, L.tmw_w2, e->tmo_xl, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
+    else OWC_TRY(launch_gemm_wide<WEPI_RES_STATS>(c, e->tm_f, L.tmw_w2, e->tmo_xl, e->tmo_xb, g, OWC_KCAT_GEMM_FFN2, f2_splits));
   }
   const LayerW& LL = e->layers[a.layers - 1];
   {
     ProfScope prof(c, OWC_KCAT_POOL);
-    DISPATCH_NV(H, k_pool_ln_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->x, e->st2, res_slots, stride, LL.ln2g, LL.ln2b, a.ln_eps, d_cu, seq0, n_seq,
+    DISPATCH_NV(H, k_pool_ln_l2<NV><<<(n_seq + 3) / 4, 128, 0, c->stream>>>(e->xb, e->xl, e->st2, res_slots, stride, LL.ln2g, LL.ln2b, a.ln_eps, d_cu, seq0, n_seq,
                                                                            tok0, H, z, zb));
   }
   OWC_TRY(check_launch(c, "k_pool_ln_l2"));

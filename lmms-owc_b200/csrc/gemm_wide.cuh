@@ -40,7 +40,7 @@ namespace owc {
 enum : int {
   WEPI_FOLD_BF16 = 0,        // out bf16 = rstd_r * (acc - mu_r * c1[n]) + c2[n]
   WEPI_FOLD_GELU_BF16 = 1,   // out bf16 = gelu_erf(the same)
-  WEPI_RES_STATS = 2,        // y = acc + bias[n] + LN_prev(y) in place (fp32) + bf16 copy; row (sum, sumsq) left in slots
+  WEPI_RES_STATS = 2,        // y = acc + bias[n] + LN_prev(y) in place, y as a bf16 pair hi | lo (tmD | tmC); row (sum, sumsq) left in slots
   WEPI_RES_STATS_DEEP = 3    // the same for long K (FFN2, K = 3072): a 5-stage operand ring paid for with a single residual
                              // buffer per warp (the residual fetch is exposed, which a 24 k clk column tile hides easily)
 };
@@ -58,7 +58,6 @@ struct WideArgs {
   const float* stats_in;     // [slots_in][stat_stride][2] partial (sum, sumsq) of the A operand's pre-LayerNorm rows
   // WEPI_RES_STATS
   const float* bias;         // [N]
-  float* y;                  // [M, N] fp32 residual stream, updated in place
   const float* stats_prev;   // partial statistics of y on entry (same layout, slots_in slots)
   const float* gamma_prev;   // [N] LayerNorm that turns y (on entry) into the residual
   const float* beta_prev;
@@ -79,10 +78,10 @@ struct WideCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;          // 32 KB
-  // per epilogue warp. fold: 2 x 2 KB bf16 output tiles. res: 2 x 4 KB fp32 tiles (the residual chunk lands here by TMA,
-  // is updated in place and TMA-stored back) + one 2 KB bf16 tile
+  // per epilogue warp. fold: 2 x 2 KB bf16 output tiles. res: 2 x 4 KB = the hi | lo bf16 tiles of a residual chunk (they land
+  // here by TMA, are updated in place and TMA-stored back)
   static constexpr int RES_BUFS = EPI == WEPI_RES_STATS ? 2 : 1;
-  static constexpr int STG_WARP = (EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP) ? RES_BUFS * 4096 + 2048 : 2 * 2048;
+  static constexpr int STG_WARP = (EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP) ? RES_BUFS * 4096 : 2 * 2048;
   static constexpr int STAGES = EPI == WEPI_RES_STATS ? 4 : 5;
   static constexpr int PARAM_BYTES = 2 * 3 * BN * 4;              // [tile parity][3 column vectors][BN]
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + kEpiWarps * STG_WARP + 512 + PARAM_BYTES;
@@ -100,7 +99,6 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr bool RES = EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP;
   constexpr int RB = Cfg::RES_BUFS;             // res: fp32 residual / output buffers per epilogue warp
-  constexpr int BBUF = Cfg::RES_BUFS * 4096;    // res: offset of the warp's bf16 output tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -279,7 +277,8 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto fetch_res = [&](int n0) {   // lane 0; the buffer's previous TMA store has finished reading it (see below)
           uint64_t* rb = &rbar[(warp - 2) * 2 + (res_n % RB)];
           mbar_expect_tx(rb, 4096u);
-          tma_load_2d(stg + (res_n % RB) * 4096, &tmC, rb, n0, row0);
+          tma_load_2d(stg + (res_n % RB) * 4096, &tmD, rb, n0, row0);          // hi tile (32 x 32 bf16, SWIZZLE_64B)
+          tma_load_2d(stg + (res_n % RB) * 4096 + 2048, &tmC, rb, n0, row0);   // lo tile
         };
         if constexpr (RES) {
           if (j == 0) {
@@ -322,30 +321,48 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
             mbar_wait(rb, rpar);
-            uint8_t* rowp = fbuf + lane * 128;
-            const int sw = lane & 7;
+            uint8_t* hrow = fbuf + lane * 64;           // this thread's row of the hi tile, of the lo tile
+            uint8_t* lrow = fbuf + 2048 + lane * 64;
+            const int sw = (lane >> 1) & 3;             // SWIZZLE_64B, as TMA wrote the tiles
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4));   // SWIZZLE_128B, as TMA wrote it
-              const float4 r = *cell;
-              const float4 b = *reinterpret_cast<const float4*>(p0 + c * 32 + 4 * j);
-              const float4 gm = *reinterpret_cast<const float4*>(p0 + BN + c * 32 + 4 * j);
-              const float4 bt = *reinterpret_cast<const float4*>(p0 + 2 * BN + c * 32 + 4 * j);
-              const float x0 = __uint_as_float(vc[4 * j + 0]) + b.x + fmaf(fmaf(r.x, ra, rb_), gm.x, bt.x);
-              const float x1 = __uint_as_float(vc[4 * j + 1]) + b.y + fmaf(fmaf(r.y, ra, rb_), gm.y, bt.y);
-              const float x2 = __uint_as_float(vc[4 * j + 2]) + b.z + fmaf(fmaf(r.z, ra, rb_), gm.z, bt.z);
-              const float x3 = __uint_as_float(vc[4 * j + 3]) + b.w + fmaf(fmaf(r.w, ra, rb_), gm.w, bt.w);
-              sum += (x0 + x1) + (x2 + x3);
-              sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
-              *cell = make_float4(x0, x1, x2, x3);
-              f[4 * j + 0] = x0; f[4 * j + 1] = x1; f[4 * j + 2] = x2; f[4 * j + 3] = x3;
+            for (int j = 0; j < 4; ++j) {               // 16-byte units of 8 columns
+              uint4* hc = reinterpret_cast<uint4*>(hrow + ((j ^ sw) << 4));
+              uint4* lc = reinterpret_cast<uint4*>(lrow + ((j ^ sw) << 4));
+              const uint4 hv = *hc, lv = *lc;
+              float r[8];
+              join_bf16x2(hv.x, lv.x, r[0], r[1]);
+              join_bf16x2(hv.y, lv.y, r[2], r[3]);
+              join_bf16x2(hv.z, lv.z, r[4], r[5]);
+              join_bf16x2(hv.w, lv.w, r[6], r[7]);
+              float x[8];
+#pragma unroll
+              for (int q4 = 0; q4 < 2; ++q4) {
+                const float4 b = *reinterpret_cast<const float4*>(p0 + c * 32 + 8 * j + 4 * q4);
+                const float4 gm = *reinterpret_cast<const float4*>(p0 + BN + c * 32 + 8 * j + 4 * q4);
+                const float4 bt = *reinterpret_cast<const float4*>(p0 + 2 * BN + c * 32 + 8 * j + 4 * q4);
+                x[4 * q4 + 0] = __uint_as_float(vc[8 * j + 4 * q4 + 0]) + b.x + fmaf(fmaf(r[4 * q4 + 0], ra, rb_), gm.x, bt.x);
+                x[4 * q4 + 1] = __uint_as_float(vc[8 * j + 4 * q4 + 1]) + b.y + fmaf(fmaf(r[4 * q4 + 1], ra, rb_), gm.y, bt.y);
+                x[4 * q4 + 2] = __uint_as_float(vc[8 * j + 4 * q4 + 2]) + b.z + fmaf(fmaf(r[4 * q4 + 2], ra, rb_), gm.z, bt.z);
+                x[4 * q4 + 3] = __uint_as_float(vc[8 * j + 4 * q4 + 3]) + b.w + fmaf(fmaf(r[4 * q4 + 3], ra, rb_), gm.w, bt.w);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; k += 4) {
+                sum += (x[k] + x[k + 1]) + (x[k + 2] + x[k + 3]);
+                sq = fmaf(x[k], x[k], sq); sq = fmaf(x[k + 1], x[k + 1], sq); sq = fmaf(x[k + 2], x[k + 2], sq); sq = fmaf(x[k + 3], x[k + 3], sq);
+              }
+              uint4 ho, lo;
+              split_bf16x2(x[0], x[1], ho.x, lo.x);
+              split_bf16x2(x[2], x[3], ho.y, lo.y);
+              split_bf16x2(x[4], x[5], ho.z, lo.z);
+              split_bf16x2(x[6], x[7], ho.w, lo.w);
+              *hc = ho;                                  // in place: both tiles go back from the buffer they came into
+              *lc = lo;
             }
-            stage_chunk<EPI_BIAS_BF16>(stg + BBUF, lane, f);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, fbuf, n0, row0);
-              tma_store_2d(&tmD, stg + BBUF, n0, row0);
+              tma_store_2d(&tmD, fbuf, n0, row0);
+              tma_store_2d(&tmC, fbuf + 2048, n0, row0);
               bulk_commit_group();
               if (RB == 1 && more) {        // one buffer: the next chunk can only come in once this store has read it
                 bulk_wait_group_read<0>();

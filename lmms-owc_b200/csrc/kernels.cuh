@@ -108,7 +108,8 @@ struct EmbedArgs {
   float* x;                  // [chunk tokens, H] fp32 residual stream
   __nv_bfloat16* xb;         // bf16 operand copy, or nullptr in check mode
   int* status;               // bit 0: an id was out of range (clamped)
-  float* stats;              // wide path: [chunk tokens][2] row (sum, sumsq); x / xb then hold the UN-normalised sum
+  float* stats;              // wide path: [chunk tokens][2] row (sum, sumsq); the stream then is the UN-normalised sum
+  __nv_bfloat16* xl;         // wide path: the stream as a bf16 PAIR, xb = bf16(v) and xl = bf16(v - xb) (16 mantissa bits), no fp32 copy
 };
 
 // One warp per sequence; tokens visited in order so MPNet's position id (running count of
@@ -182,11 +183,11 @@ __global__ void __launch_bounds__(128) k_embed_ln(const EmbedArgs a) {
         const int c4 = lane + 32 * i;
         s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
         q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
-        reinterpret_cast<float4*>(a.x + row * a.H)[c4] = x[i];
-        uint2 p;
-        p.x = pack_bf16x2(x[i].x, x[i].y);
-        p.y = pack_bf16x2(x[i].z, x[i].w);
+        uint2 p, l;
+        split_bf16x2(x[i].x, x[i].y, p.x, l.x);
+        split_bf16x2(x[i].z, x[i].w, p.y, l.y);
         reinterpret_cast<uint2*>(a.xb + row * a.H)[c4] = p;
+        reinterpret_cast<uint2*>(a.xl + row * a.H)[c4] = l;
       }
       s = warp_sum(s);
       q = warp_sum(q);
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(128) k_pool_l2(const float* __restrict__ x, co
 // sequence's tokens of LN(y_t) is gamma * mean_t((y_t - mu_t) * rstd_t) + beta, so the LayerNorm costs one FMA per
 // element on the way into the pooling sum. Then the same masked mean + L2 as k_pool_l2.
 template <int NV>
-__global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y, const float* __restrict__ stats, int slots,
+__global__ void __launch_bounds__(128) k_pool_ln_l2(const __nv_bfloat16* __restrict__ yh, const __nv_bfloat16* __restrict__ yl,
+                                                    const float* __restrict__ stats, int slots,
                                                     long long stat_stride, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta,
                                                     float eps, const int32_t* __restrict__ cu, int seq0, int n_seq, int tok0,
@@ -402,10 +404,14 @@ __global__ void __launch_bounds__(128) k_pool_ln_l2(const float* __restrict__ y,
     const float mu = st.x * inv_h;
     const float ra = rsqrtf(fmaxf(st.y * inv_h - mu * mu, 0.f) + eps);
     const float rb = -mu * ra;
-    const float4* r4 = reinterpret_cast<const float4*>(y + static_cast<size_t>(t) * H);
+    const uint2* h2 = reinterpret_cast<const uint2*>(yh + static_cast<size_t>(t) * H);
+    const uint2* l2 = reinterpret_cast<const uint2*>(yl + static_cast<size_t>(t) * H);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 v = r4[lane + 32 * i];
+      const uint2 hh = h2[lane + 32 * i], ll = l2[lane + 32 * i];
+      float4 v;
+      join_bf16x2(hh.x, ll.x, v.x, v.y);
+      join_bf16x2(hh.y, ll.y, v.z, v.w);
       acc[i].x += fmaf(v.x, ra, rb); acc[i].y += fmaf(v.y, ra, rb); acc[i].z += fmaf(v.z, ra, rb); acc[i].w += fmaf(v.w, ra, rb);
     }
   }
