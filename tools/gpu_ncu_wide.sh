@@ -4,11 +4,11 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 BENCH="python bench.py --rows 60000 --steps 1 --warmup 3 --sub '' --no-cpu-baseline --no-sim-leg"
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$TAG.csv \
+[ -n "$SKIP_LIST" ] || timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$TAG.csv \
     $BENCH > gpurun_out/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
 python tools/launch_summary.py gpurun_out/launches_$TAG.csv > gpurun_out/launch_summary_$TAG.txt; cat gpurun_out/launch_summary_$TAG.txt
-# class-name encode first; skip into the prediction chunks: 3 k_gemm_wide shapes x 2 layers, one k_qkv_attn
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_wide -s 42 -c 6 -o gpurun_out/prof_wide_$TAG -f \
+# class-name encode first; skip into the prediction chunks: the 3 k_gemm_wide shapes of one layer, one k_qkv_attn (gpurun brings back at most 64 MiB)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_wide -s 42 -c 3 -o gpurun_out/prof_wide_$TAG -f \
     $BENCH > gpurun_out/ncu_wide_$TAG.log 2>&1; echo "ncu k_gemm_wide rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_qkv_attn -s 14 -c 1 -o gpurun_out/prof_qkvattn_$TAG -f \
     $BENCH > gpurun_out/ncu_qkvattn_$TAG.log 2>&1; echo "ncu k_qkv_attn rc=$?"
