@@ -19,8 +19,10 @@ tok = HostTokenizer(vocab, "mpnet")
 eng = Engine(arch, random_state_dict(arch), device=0)
 cids, ccu = tok.encode_packed(cls)
 zc = eng.encode(cids, ccu, out="device")
-# short labels + a 40-token and a 60-token row (32- and 64-row attention tiles) + a one-word row
-pids, pcu = tok.encode_packed(preds + [" ".join(words[:30]), " ".join(words[:50]), "a"])
+# short labels + a 40-token and a 60-token row (32- and 64-row attention tiles: the kernel variant with out-of-line long tiles)
+# + a one-word row; with OWC_SANITIZE_SHORT=1 only short rows (the variant every label set of the benchmark runs)
+extra = ["a b", "c", "a"] if os.environ.get("OWC_SANITIZE_SHORT") == "1" else [" ".join(words[:30]), " ".join(words[:50]), "a"]
+pids, pcu = tok.encode_packed(preds + extra)
 res = eng.score(pids, pcu, zc, targets=np.asarray(targets + [0, 1, 2], np.int32), k=5)
 print("ok", res["scores"].shape, float(res["paired"].mean()), "launches", eng.stats()["kernel_launches"])
 eng.close()
