@@ -328,3 +328,28 @@ def test_qkv_attention_kernel_on_ragged_lengths(mpnet, monkeypatch, seed, lo, hi
     finally:
         fused.close()
         split.close()
+
+
+def test_qkv_attention_early_release_is_stable_at_scale(mpnet, monkeypatch):
+    """k_qkv_attn gives the q|k|v rows of a head back to the drain warps as soon as every attention warp holds its unit in
+    registers (one shared buffer). A hole in that hand-over would show as run-to-run differences on a launch that keeps all
+    148 SMs busy for many heads: several chunks of label-length sequences, six runs, every run bit-identical, and equal to
+    the separate-kernel path within bf16 noise."""
+    b = mpnet
+    rng = np.random.default_rng(11)
+    lens = rng.integers(1, 17, size=48_000)                      # ~400 k tokens: three chunks of 1 184 row blocks
+    ids = rng.integers(5, b.arch.vocab - 1, size=int(lens.sum())).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    monkeypatch.setenv("OWC_QKV_ATTN", "1")
+    fused = Engine(b.arch, b.sd, device=0)
+    monkeypatch.setenv("OWC_QKV_ATTN", "0")
+    split = Engine(b.arch, b.sd, device=0)
+    try:
+        z0 = fused.encode(ids, cu)
+        assert np.isfinite(z0).all()
+        for _ in range(5):
+            assert np.array_equal(z0, fused.encode(ids, cu))
+        assert np.abs(z0 - split.encode(ids, cu)).max() < 2e-3
+    finally:
+        fused.close()
+        split.close()
