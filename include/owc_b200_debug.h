@@ -37,11 +37,15 @@ int32_t owc_bench_sim_kernel(owc_ctx* ctx, int64_t n, int32_t c, int32_t dim, in
  * LayerNorm 2 done. Copies the 2048 int64 debug words (stamps, phase sums, event traces) of the most recent launch to `stamps` (HOST).      */
 int32_t owc_debug_fused_stamps(owc_encoder* enc, int64_t* stamps);
 
-/* Debug: cycle counters of the instrumented persistent GEMM (gemm_wide.cuh), available when the ctx was created with
- * OWC_WIDE_DBG=1: 32 int64 = [epilogue kind 0..3][8] {0: MMA warp waiting for operands, 1: waiting for a free accumulator,
- * 2: MMA warp total, 3: epilogue warp waiting for an accumulator, 4: epilogue warp total, 5: leader CTAs counted}, summed
- * over launches since the last reset.                                                                              */
-int32_t owc_debug_wide_counters(owc_ctx* ctx, int64_t* out32, int32_t reset);
+/* Debug: cycle counters of the instrumented persistent kernels of the wide path, available when the ctx was created with
+ * OWC_WIDE_DBG=1: 48 int64, summed over launches since the last reset.
+ *   [epilogue kind 0..3][8] of k_gemm_wide (gemm_wide.cuh): {0: MMA warp waiting for operands, 1: waiting for a free accumulator,
+ *     2: MMA warp total, 3: epilogue warp waiting for an accumulator, 4: epilogue warp total, 5: leader CTAs counted};
+ *   [32..47] of k_qkv_attn (qkv_attn.cuh): {32: MMA warp waiting for operands, 33: for a free accumulator, 34: MMA warp total,
+ *     35: drain warp 0 waiting for an accumulator, 36: for the q|k|v buffer, 37: drain warp 0 total, 38: leader CTAs counted,
+ *     39: attention units of attention warp 0, 40: that warp waiting for the rows, 41: building the block's tables, 42: total,
+ *     43..47: its time in the phases of a unit (fragment loads, Q K^T, softmax, P V, output stores)}.                      */
+int32_t owc_debug_wide_counters(owc_ctx* ctx, int64_t* out48, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -1735,11 +1735,11 @@ extern "C" int32_t owc_debug_fused_stamps(owc_encoder* e, int64_t* out64) {
   return 0;
 }
 
-extern "C" int32_t owc_debug_wide_counters(owc_ctx* c, int64_t* out32, int32_t reset) {
-  if (!c || !out32) return fail("owc_debug_wide_counters: NULL argument");
+extern "C" int32_t owc_debug_wide_counters(owc_ctx* c, int64_t* out48, int32_t reset) {
+  if (!c || !out48) return fail("owc_debug_wide_counters: NULL argument");
   if (!c->wide_dbg) return fail("the ctx was not created with OWC_WIDE_DBG=1");
   CU_OK(cudaSetDevice(c->device));
-  CU_OK(cudaMemcpyAsync(out32, c->wide_dbg, 48 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaMemcpyAsync(out48, c->wide_dbg, 48 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   if (reset) CU_OK(cudaMemsetAsync(c->wide_dbg, 0, 48 * sizeof(long long), c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
   return 0;
