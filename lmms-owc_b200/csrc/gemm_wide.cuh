@@ -80,6 +80,8 @@ struct WideCfg {
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;          // 32 KB
   // per epilogue warp. fold: 2 x 2 KB bf16 output tiles. res: 2 x 4 KB = the hi | lo bf16 tiles of a residual chunk (they land
   // here by TMA, are updated in place and TMA-stored back)
+  // O-projection: 2 buffers + 4 ring stages. Measured on one box: 1 buffer (and 5 stages) 45.7 ms per 300 k rows, 2 buffers
+  // 35.8 ms, 3 buffers (which leave 3 ring stages) 36.6 ms.
   static constexpr int RES_BUFS = EPI == WEPI_RES_STATS ? 2 : 1;
   static constexpr int STG_WARP = (EPI == WEPI_RES_STATS || EPI == WEPI_RES_STATS_DEEP) ? RES_BUFS * 4096 : 2 * 2048;
   static constexpr int STAGES = EPI == WEPI_RES_STATS ? 4 : 5;
@@ -109,7 +111,7 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);   // [kEpiWarps][2] res: residual chunk landed in the warp's fp32 buffer
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(tail + 256);   // [kEpiWarps][3] res: residual chunk (hi | lo tiles) landed in one of the warp's buffers
   float* param_s = reinterpret_cast<float*>(tail + 512);   // [2][3][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -130,7 +132,7 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * kEpiWarps); }
     if constexpr (RES) {
-      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
+      for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     }
     fence_barrier_init();
   }
@@ -274,17 +276,26 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // the warp's two fp32 buffers, one chunk ahead; the thread updates its row in place and the buffer is TMA-stored back
         // over y. (Row-per-thread global loads cost 32 LSU wavefronts per instruction: 8 warps x 4 chunks x 256 wavefronts per
         // column tile exceeded the 6.1 k clk the O-projection's MMAs take and held that kernel at 0.46 PFLOP/s.)
-        auto fetch_res = [&](int n0) {   // lane 0; the buffer's previous TMA store has finished reading it (see below)
-          uint64_t* rb = &rbar[(warp - 2) * 2 + (res_n % RB)];
+        // Buffers are used round-robin by the warp's running chunk count (seq); the fetch runs LA = RB - 1 chunks ahead of the
+        // arithmetic (one chunk ahead is less than a DRAM round trip: with a single buffer the O-projection takes 30 % longer).
+        constexpr int LA = RB - 1;
+        const int n_chunks = nt * NCW;
+        auto chunk_col = [&](int k) {            // first column of chunk k of this item (k = tile step * NCW + chunk step)
+          const int jj = k / NCW, cc = k - jj * NCW;
+          return (tile0 + (jj + rot) % nt) * BN + (2 * cc + half) * 32;
+        };
+        auto fetch_seq = [&](uint32_t seq, int n0) {   // lane 0; the buffer's previous TMA stores have finished reading it
+          uint64_t* rb = &rbar[(warp - 2) * 3 + (seq % RB)];
+          uint8_t* b = stg + (seq % RB) * 4096;
           mbar_expect_tx(rb, 4096u);
-          tma_load_2d(stg + (res_n % RB) * 4096, &tmD, rb, n0, row0);          // hi tile (32 x 32 bf16, SWIZZLE_64B)
-          tma_load_2d(stg + (res_n % RB) * 4096 + 2048, &tmC, rb, n0, row0);   // lo tile
+          tma_load_2d(b, &tmD, rb, n0, row0);          // hi tile (32 x 32 bf16, SWIZZLE_64B)
+          tma_load_2d(b + 2048, &tmC, rb, n0, row0);   // lo tile
         };
         if constexpr (RES) {
           if (j == 0) {
             if (lane == 0) {
-              bulk_wait_group_read<0>();   // the previous item's stores have read both buffers
-              fetch_res(tile * BN + half * 32);
+              bulk_wait_group_read<0>();   // the previous item's stores have read every buffer
+              for (int i = 0; i < (LA > 0 ? LA : 1) && i < n_chunks; ++i) fetch_seq(res_n + i, chunk_col(i));
             }
             __syncwarp();
           }
@@ -309,15 +320,14 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float f[32];
           if constexpr (RES) {
             uint8_t* fbuf = stg + (res_n % RB) * 4096;
-            uint64_t* rb = &rbar[(warp - 2) * 2 + (res_n % RB)];
+            uint64_t* rb = &rbar[(warp - 2) * 3 + (res_n % RB)];
             const uint32_t rpar = (res_n / RB) & 1u;
+            const uint32_t seq = res_n;
             ++res_n;
-            // next chunk of this item (same tile, or the first chunk of the next tile)
-            const bool more = cw + 1 < NCW || j + 1 < nt;
-            const int n_next = cw + 1 < NCW ? n0 + 64 : tile_next * BN + half * 32;
+            const int k = j * NCW + cw;        // this chunk's index within the item
             if (lane == 0) {
-              bulk_wait_group_read<0>();   // the other buffer's last store (one chunk ago) and the bf16 tile's have read them
-              if (RB == 2 && more) fetch_res(n_next);   // two buffers: one chunk ahead, under this chunk's arithmetic
+              bulk_wait_group_read<0>();   // the stores of the chunk before this one have read their buffer: it takes chunk k + LA
+              if (LA > 0 && k + LA < n_chunks) fetch_seq(seq + LA, chunk_col(k + LA));
             }
             __syncwarp();
             mbar_wait(rb, rpar);
@@ -364,9 +374,9 @@ k_gemm_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_store_2d(&tmD, fbuf, n0, row0);
               tma_store_2d(&tmC, fbuf + 2048, n0, row0);
               bulk_commit_group();
-              if (RB == 1 && more) {        // one buffer: the next chunk can only come in once this store has read it
+              if (RB == 1 && k + 1 < n_chunks) {   // one buffer: the next chunk can only come in once this store has read it
                 bulk_wait_group_read<0>();
-                fetch_res(n_next);
+                fetch_seq(seq + 1, chunk_col(k + 1));
               }
             }
           } else {
