@@ -54,8 +54,8 @@ for waves in waves_list:
                 aqf, atbl, atot = (int(x) for x in c[5][:3])
                 units = max(int(c[4][7]), 1)
                 phs = [int(x) for x in c[5][3:8]]
-                print(f"  k_qkv_attn attention warp 0: {units} units, clk per unit: bounds {phs[0] / units:.0f}, QK {phs[1] / units:.0f}, softmax {phs[2] / units:.0f}, "
-                      f"PV {phs[3] / units:.0f}, rows to shared {phs[4] / units:.0f}, write-back + loop {(atot - aqf - atbl - sum(phs)) / units:.0f}", flush=True)
+                print(f"  k_qkv_attn attention warp 0: {units} units, clk per unit: fragment loads + release {phs[0] / units:.0f}, QK {phs[1] / units:.0f}, softmax {phs[2] / units:.0f}, "
+                      f"PV {phs[3] / units:.0f}, output stores {phs[4] / units:.0f}, loop {(atot - aqf - atbl - sum(phs)) / units:.0f}", flush=True)
                 tiles = n_tok / 100.0   # only for scale
                 print(f"  k_qkv_attn: MMA warp ring wait {ring / tot:6.1%}  accumulator wait {acc / tot:6.1%}  issue {1 - (ring + acc) / tot:6.1%} | "
                       f"drain warp 0: accumulator wait {dtf / dtot:6.1%}  q|k|v buffer wait {dqf / dtot:6.1%}  work {1 - (dtf + dqf) / dtot:6.1%} | "
