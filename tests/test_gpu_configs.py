@@ -353,3 +353,41 @@ def test_qkv_attention_early_release_is_stable_at_scale(mpnet, monkeypatch):
     finally:
         fused.close()
         split.close()
+
+
+@pytest.mark.parametrize("case", ["empties", "one_token_rows", "full_blocks", "single_row", "odd_blocks"])
+def test_qkv_attention_kernel_block_edges(mpnet, monkeypatch, case):
+    """Row-block packing edges of k_qkv_attn on the wide path: empty sequences between labels (NaN rows, as `_text.py:202`
+    has no epsilon), blocks closed by the 128-sequence cap (one-token rows: eight units of sixteen sequences), sequences
+    that fill blocks exactly, a single row, an odd number of blocks (the pair's second CTA idles). Against the
+    separate-kernel path."""
+    b = mpnet
+    rng = np.random.default_rng(5)
+    if case == "empties":
+        lens = rng.integers(0, 9, size=3000)
+        lens[::7] = 0
+    elif case == "one_token_rows":
+        lens = np.ones(1000, np.int64)
+        lens[500:] = rng.integers(1, 4, size=500)
+    elif case == "full_blocks":
+        lens = np.asarray([16] * 64 + [8] * 32 + [64, 64] * 3 + [5] * 40, np.int64)
+    elif case == "single_row":
+        lens = np.asarray([7], np.int64)
+    else:
+        lens = np.asarray([16] * 8 * 3, np.int64)          # exactly three blocks
+    ids = rng.integers(5, b.arch.vocab - 1, size=int(lens.sum())).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    monkeypatch.setenv("OWC_QKV_ATTN", "1")
+    fused = Engine(b.arch, b.sd, device=0)
+    monkeypatch.setenv("OWC_QKV_ATTN", "0")
+    split = Engine(b.arch, b.sd, device=0)
+    try:
+        z1, z0 = fused.encode(ids, cu), split.encode(ids, cu)
+        empty = lens == 0
+        assert np.isnan(z1[empty]).all() and np.isnan(z0[empty]).all()
+        assert np.isfinite(z1[~empty]).all()
+        assert np.abs(z1[~empty] - z0[~empty]).max() < 2e-3
+        assert np.array_equal(z1[~empty], fused.encode(ids, cu)[~empty])
+    finally:
+        fused.close()
+        split.close()
